@@ -1,0 +1,154 @@
+/*
+ * nlam_b200.h — C ABI of libnlam_b200.so: B200 (sm_100a) kernels for the Neural-LAM
+ * InteractionNet message-passing hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native code at all: the path is
+ * Python calling torch_geometric.  Each entry point below names the reference interface
+ * it replaces (paths relative to the reference repo, mllam/neural-lam @ 434d5fab):
+ *
+ *   nlam_graph_create        <- InteractionNet.__init__ edge_index handling
+ *                               (neural_lam/gnn_layers.py:73-86)
+ *   nlam_inet_fwd            <- InteractionNet.forward / PropagationNet
+ *                               (neural_lam/gnn_layers.py:110-157, :231-249) incl. PyG
+ *                               MessagePassing.propagate/aggregate (gnn_layers.py:145,:188)
+ *   nlam_rowmlp_fwd          <- utils.make_mlp networks (neural_lam/utils/networks.py:27-40)
+ *                               as used by embedders / grid MLPs
+ *                               (models/step_predictors/graph/base.py:286-310, :322)
+ *   nlam_segment_sum         <- PyG SumAggregation/MeanAggregation (scatter_add_) reached
+ *                               from gnn_layers.py:188; also the backward of the gathers
+ *   nlam_gather_rows         <- x.index_select(-2, edge_index[k]) in PyG propagate
+ *   nlam_step_epilogue       <- rescale + residual + boundary mix
+ *                               (graph/base.py:339-342, forecasters/autoregressive.py:128-131)
+ *
+ * Conventions
+ *   - All tensors are device pointers owned by the caller (PyTorch), fp32, row-major with
+ *     the feature dimension contiguous; a "batch stride" is in ELEMENTS and may be 0 for
+ *     batch-broadcast (torch.expand) inputs (reference expand_to_batch,
+ *     models/step_predictors/base.py:122-139).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*);
+ *     no entry point synchronises the device.
+ *   - Return value: 0 on success, non-zero error code otherwise (NLAM_E_*), with a message
+ *     retrievable through nlam_last_error().  Nothing throws or exits across the ABI.
+ *   - There is no CPU fallback: calls fail with NLAM_E_CUDA if no device is usable.
+ */
+#ifndef NLAM_B200_H
+#define NLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLAM_ABI_VERSION 1
+
+/* error codes */
+#define NLAM_OK 0
+#define NLAM_E_INVALID 1     /* bad argument / shape */
+#define NLAM_E_UNSUPPORTED 2 /* shape not supported by the requested kernel family */
+#define NLAM_E_CUDA 3        /* CUDA runtime/driver error */
+#define NLAM_E_WORKSPACE 4   /* workspace too small */
+
+/* flags for nlam_inet_fwd / nlam_rowmlp_fwd */
+#define NLAM_AGGR_MEAN 0x1        /* mean instead of sum aggregation */
+#define NLAM_PROPAGATION 0x2      /* PropagationNet: msg = x_j + mlp(..), node residual = aggr */
+#define NLAM_MATH_TF32 0x10       /* tcgen05 TF32 tensor-core kernels (fp32 accumulate) */
+#define NLAM_MATH_FP32 0x20       /* exact fp32 FFMA kernels */
+/* neither math flag: TF32 when the shape is supported by the tensor-core kernels, else FP32 */
+
+#define NLAM_MAX_LINEAR 4
+#define NLAM_MAX_SRC 3
+
+/* One make_mlp network: Linear -> SiLU -> ... -> Linear [-> LayerNorm].
+ * w[l] is the nn.Linear weight (out_dim[l], in_dim[l]) row-major, b[l] its bias. */
+typedef struct NlamMlp {
+  int32_t n_linear;                 /* hidden_layers + 1 */
+  int32_t in_dim;                   /* input width of w[0] */
+  int32_t out_dim[NLAM_MAX_LINEAR]; /* output width of each Linear */
+  const float* w[NLAM_MAX_LINEAR];
+  const float* b[NLAM_MAX_LINEAR];
+  const float* ln_gamma; /* NULL: no LayerNorm */
+  const float* ln_beta;
+  float ln_eps;
+  int32_t _pad;
+} NlamMlp;
+
+/* One input block of a row-MLP: rows of width `dim`, optionally gathered through idx. */
+typedef struct NlamRowSrc {
+  const float* ptr;
+  const int32_t* idx; /* NULL: row r reads row r; else row r reads row idx[r] */
+  int64_t bstride;    /* elements between batches (0 = broadcast) */
+  int32_t dim;        /* width; rows are contiguous with pitch `dim` */
+  int32_t _pad;
+} NlamRowSrc;
+
+typedef struct NlamGraph NlamGraph; /* opaque: receiver-sorted CSR (+ sender CSR) of one edge set */
+
+/* library info */
+int nlam_abi_version(void);
+const char* nlam_last_error(void);
+const char* nlam_build_info(void);
+
+/* Build the device CSR of one edge set.  edge_index is a HOST pointer to the (2,E) int64
+ * array the reference passes to InteractionNet (row 0 senders, row 1 receivers, both
+ * zero-based in their own node set).  num_rec = max(receiver)+1 as the reference infers it
+ * (gnn_layers.py:73) unless n_rec_hint > that. */
+int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int64_t n_edges,
+                      int64_t n_rec_hint, int device);
+void nlam_graph_destroy(NlamGraph* g);
+int64_t nlam_graph_num_edges(const NlamGraph* g);
+int64_t nlam_graph_num_rec(const NlamGraph* g);
+int64_t nlam_graph_num_send(const NlamGraph* g);   /* max(sender)+1 */
+int32_t nlam_graph_max_in_degree(const NlamGraph* g);
+int32_t nlam_graph_is_sorted(const NlamGraph* g);   /* 1 if the given order already is CSR order */
+/* device pointers (int32): receiver CSR, sender CSR (for gather backward), permutations */
+const int32_t* nlam_graph_rowptr(const NlamGraph* g);   /* (num_rec+1) */
+const int32_t* nlam_graph_src(const NlamGraph* g);      /* (E) sender of CSR-ordered edge k */
+const int32_t* nlam_graph_dst(const NlamGraph* g);      /* (E) receiver of CSR-ordered edge k */
+const int32_t* nlam_graph_perm(const NlamGraph* g);     /* (E) original edge id of CSR edge k */
+const int32_t* nlam_graph_inv_perm(const NlamGraph* g); /* (E) CSR position of original edge i */
+const int32_t* nlam_graph_sptr(const NlamGraph* g);     /* (num_send+1) sender CSR offsets */
+const int32_t* nlam_graph_sperm(const NlamGraph* g);    /* (E) CSR-order edge ids grouped by sender */
+
+/* Workspace (bytes) nlam_inet_fwd needs for batch B and width H. */
+size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, int flags);
+
+/* One InteractionNet / PropagationNet forward.  `edge` and `edge_out` are in CSR edge order
+ * (nlam_graph_perm); send (B,Ns,H), rec (B,Nr,H), edge (B,E,H), rec_out (B,Nr,H),
+ * edge_out (B,E,H) or NULL (update_edges=False).  aggr_out (B,Nr,H) may be NULL (then it
+ * lives in the workspace); out strides are dense. */
+int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
+                  const float* send, int64_t send_bstride, const float* rec, int64_t rec_bstride,
+                  const float* edge, int64_t edge_bstride, float* rec_out, float* edge_out,
+                  float* aggr_out, int B, int flags, void* workspace, size_t ws_bytes,
+                  void* stream);
+
+/* out[b,r,:] = (res ? res[b, ridx ? ridx[r] : r, :] : 0) + MLP(concat_s src_s[b, idx_s[r], :])
+ * for r in [0,n_rows); out2 (nullable) = res2[b,r,:] + out[b,r,:]. */
+int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                    const NlamRowSrc* res2, float* out, float* out2, int64_t n_rows, int B,
+                    int flags, void* stream);
+
+/* out[b,n,:] = scale_n * sum_{k in [ptr[n],ptr[n+1])} x[b, order ? order[k] : k, :]
+ * scale_n = 1 (sum) or 1/max(deg,1) (mean).  Deterministic, CSR order. */
+int nlam_segment_sum(const int32_t* ptr, const int32_t* order, int64_t n_seg, const float* x,
+                     int64_t x_bstride, float* out, int64_t out_bstride, int B, int H, int mean,
+                     void* stream);
+
+/* out[b,r,:] = scale * x[b, idx[r], :]   (scale_by_deg_ptr: optional CSR offsets; when given,
+ * row r is additionally scaled by 1/max(deg(idx[r]),1) — backward of the mean aggregation). */
+int nlam_gather_rows(const float* x, int64_t x_bstride, const int32_t* idx, int64_t n_rows,
+                     float* out, int64_t out_bstride, int B, int H, const int32_t* deg_ptr,
+                     void* stream);
+
+/* new_state = bmask * boundary + (1-bmask) * (prev + net_out*diff_std + diff_mean)
+ * over (B,G,D); bmask (G), diff_std/mean (D); boundary may be NULL (then bmask ignored). */
+int nlam_step_epilogue(const float* net_out, const float* prev, const float* boundary,
+                       const float* bmask, const float* diff_std, const float* diff_mean,
+                       float* new_state, int64_t B, int64_t G, int64_t D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLAM_B200_H */

@@ -1,0 +1,76 @@
+// Shared declarations for libnlam_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "nlam_b200.h"
+
+namespace nlam {
+
+// thread-local last-error text (nlam_last_error)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define NLAM_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      nlam::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return NLAM_E_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define NLAM_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) {                    \
+      nlam::set_error(__VA_ARGS__);   \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+constexpr int kTileEdges = 128;  // rows of one tensor-core edge tile (UMMA M)
+
+}  // namespace nlam
+
+// Receiver-sorted CSR of one edge set + sender CSR + tensor-core tile table.
+struct NlamGraph {
+  int device = 0;
+  int64_t n_edges = 0, n_rec = 0, n_send = 0;
+  int32_t max_in_degree = 0;
+  int32_t is_sorted = 0;
+  // device arrays (int32)
+  int32_t* rowptr = nullptr;    // n_rec+1
+  int32_t* src = nullptr;       // E, sender of CSR edge k
+  int32_t* dst = nullptr;       // E, receiver of CSR edge k
+  int32_t* perm = nullptr;      // E, original edge id of CSR edge k
+  int32_t* inv_perm = nullptr;  // E
+  int32_t* sptr = nullptr;      // n_send+1
+  int32_t* sperm = nullptr;     // E
+  // tensor-core tiles: whole receivers packed into <=128-edge tiles.
+  // tile t covers receivers [tile_rec[t], tile_rec[t+1]) and edges
+  // [rowptr[tile_rec[t]], rowptr[tile_rec[t+1]]).  n_tiles == 0 if some in-degree > 128.
+  int32_t n_tiles = 0;
+  int32_t* tile_rec = nullptr;  // n_tiles+1
+  std::vector<int32_t> h_tile_rec, h_rowptr;
+};
+
+namespace nlam {
+// simt.cu
+int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                const NlamRowSrc* res2, float* out, float* out2, int64_t n_rows, int B,
+                cudaStream_t stream);
+// tc.cu
+bool tc_rowmlp_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                         const NlamRowSrc* res2, int64_t n_rows);
+int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+              float* out, int64_t n_rows, int B, cudaStream_t stream);
+bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags);
+int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs,
+            const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out,
+            float* aggr_out, int B, int flags, cudaStream_t stream);
+}  // namespace nlam

@@ -1,0 +1,162 @@
+// Graph handle: receiver-sorted CSR (stable counting sort), sender CSR, tensor-core tile table.
+// Replaces the edge_index bookkeeping of InteractionNet.__init__ (reference
+// neural_lam/gnn_layers.py:73-86) and PyG's per-call index handling.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace nlam {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+}  // namespace nlam
+
+using namespace nlam;
+
+extern "C" int nlam_abi_version(void) { return NLAM_ABI_VERSION; }
+extern "C" const char* nlam_last_error(void) { return nlam::get_error(); }
+extern "C" const char* nlam_build_info(void) {
+  return "libnlam_b200 abi=1 arch=sm_100a cuda=" __DATE__;
+}
+
+template <class T>
+static int upload(T** dptr, const std::vector<T>& h) {
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  NLAM_CUDA_OK(cudaMalloc((void**)dptr, bytes));
+  if (!h.empty()) NLAM_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return NLAM_OK;
+}
+
+extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int64_t E,
+                                 int64_t n_rec_hint, int device) {
+  NLAM_REQUIRE(out && edge_index, NLAM_E_INVALID, "nlam_graph_create: null argument");
+  NLAM_REQUIRE(E >= 1 && E < (int64_t(1) << 31), NLAM_E_INVALID, "nlam_graph_create: bad edge count %lld", (long long)E);
+  const int64_t* snd = edge_index;
+  const int64_t* rcv = edge_index + E;
+  int64_t max_r = -1, max_s = -1;
+  for (int64_t i = 0; i < E; ++i) {
+    NLAM_REQUIRE(snd[i] >= 0 && rcv[i] >= 0, NLAM_E_INVALID, "nlam_graph_create: negative index at edge %lld", (long long)i);
+    max_r = std::max(max_r, rcv[i]);
+    max_s = std::max(max_s, snd[i]);
+  }
+  NLAM_REQUIRE(max_r < (int64_t(1) << 31) - 1 && max_s < (int64_t(1) << 31) - 1, NLAM_E_INVALID, "index too large");
+  int64_t n_rec = std::max(max_r + 1, n_rec_hint);
+  int64_t n_send = max_s + 1;
+
+  NlamGraph* g = new NlamGraph();
+  g->device = device;
+  g->n_edges = E;
+  g->n_rec = n_rec;
+  g->n_send = n_send;
+
+  // stable counting sort by receiver
+  std::vector<int32_t> rowptr(n_rec + 1, 0);
+  for (int64_t i = 0; i < E; ++i) rowptr[rcv[i] + 1]++;
+  int32_t maxdeg = 0;
+  for (int64_t r = 0; r < n_rec; ++r) {
+    maxdeg = std::max(maxdeg, rowptr[r + 1]);
+    rowptr[r + 1] += rowptr[r];
+  }
+  std::vector<int32_t> cursor(rowptr.begin(), rowptr.end() - 1);
+  std::vector<int32_t> perm(E), inv_perm(E), src(E), dst(E);
+  bool sorted = true;
+  for (int64_t i = 0; i < E; ++i) {
+    int32_t k = cursor[rcv[i]]++;
+    perm[k] = (int32_t)i;
+    inv_perm[i] = k;
+    src[k] = (int32_t)snd[i];
+    dst[k] = (int32_t)rcv[i];
+    if (k != i) sorted = false;
+  }
+  g->max_in_degree = maxdeg;
+  g->is_sorted = sorted ? 1 : 0;
+
+  // sender CSR over CSR-ordered edges (stable): backward of the sender gather
+  std::vector<int32_t> sptr(n_send + 1, 0), sperm(E);
+  for (int64_t k = 0; k < E; ++k) sptr[src[k] + 1]++;
+  for (int64_t s = 0; s < n_send; ++s) sptr[s + 1] += sptr[s];
+  {
+    std::vector<int32_t> cur(sptr.begin(), sptr.end() - 1);
+    for (int64_t k = 0; k < E; ++k) sperm[cur[src[k]]++] = (int32_t)k;
+  }
+
+  // tensor-core tile table: whole receivers, <=kTileEdges edges and <=kTileEdges receivers
+  std::vector<int32_t> tile_rec;
+  if (maxdeg <= kTileEdges) {
+    tile_rec.push_back(0);
+    int64_t r = 0;
+    while (r < n_rec) {
+      int64_t r0 = r;
+      int32_t e0 = rowptr[r0];
+      while (r < n_rec && (r - r0) < kTileEdges && rowptr[r + 1] - e0 <= kTileEdges) ++r;
+      tile_rec.push_back((int32_t)r);
+    }
+    g->n_tiles = (int32_t)tile_rec.size() - 1;
+  }
+  g->h_tile_rec = tile_rec;
+  g->h_rowptr = rowptr;
+
+  int prev_dev = 0;
+  cudaError_t e = cudaGetDevice(&prev_dev);
+  if (e != cudaSuccess) {
+    set_error("nlam_graph_create: cudaGetDevice failed: %s (no CPU fallback)", cudaGetErrorString(e));
+    delete g;
+    return NLAM_E_CUDA;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("nlam_graph_create: cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+    delete g;
+    return NLAM_E_CUDA;
+  }
+  int rc = NLAM_OK;
+  if ((rc = upload(&g->rowptr, rowptr)) || (rc = upload(&g->src, src)) || (rc = upload(&g->dst, dst)) ||
+      (rc = upload(&g->perm, perm)) || (rc = upload(&g->inv_perm, inv_perm)) ||
+      (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
+      (rc = upload(&g->tile_rec, tile_rec))) {
+    cudaSetDevice(prev_dev);
+    nlam_graph_destroy(g);
+    return rc;
+  }
+  cudaSetDevice(prev_dev);
+  *out = g;
+  return NLAM_OK;
+}
+
+extern "C" void nlam_graph_destroy(NlamGraph* g) {
+  if (!g) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(g->device);
+  cudaFree(g->rowptr);
+  cudaFree(g->src);
+  cudaFree(g->dst);
+  cudaFree(g->perm);
+  cudaFree(g->inv_perm);
+  cudaFree(g->sptr);
+  cudaFree(g->sperm);
+  cudaFree(g->tile_rec);
+  cudaSetDevice(prev);
+  delete g;
+}
+
+extern "C" int64_t nlam_graph_num_edges(const NlamGraph* g) { return g->n_edges; }
+extern "C" int64_t nlam_graph_num_rec(const NlamGraph* g) { return g->n_rec; }
+extern "C" int64_t nlam_graph_num_send(const NlamGraph* g) { return g->n_send; }
+extern "C" int32_t nlam_graph_max_in_degree(const NlamGraph* g) { return g->max_in_degree; }
+extern "C" int32_t nlam_graph_is_sorted(const NlamGraph* g) { return g->is_sorted; }
+extern "C" const int32_t* nlam_graph_rowptr(const NlamGraph* g) { return g->rowptr; }
+extern "C" const int32_t* nlam_graph_src(const NlamGraph* g) { return g->src; }
+extern "C" const int32_t* nlam_graph_dst(const NlamGraph* g) { return g->dst; }
+extern "C" const int32_t* nlam_graph_perm(const NlamGraph* g) { return g->perm; }
+extern "C" const int32_t* nlam_graph_inv_perm(const NlamGraph* g) { return g->inv_perm; }
+extern "C" const int32_t* nlam_graph_sptr(const NlamGraph* g) { return g->sptr; }
+extern "C" const int32_t* nlam_graph_sperm(const NlamGraph* g) { return g->sperm; }

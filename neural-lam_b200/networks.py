@@ -1,0 +1,99 @@
+"""MLP and GNN-stack factories with the reference's interface
+(reference neural_lam/utils/networks.py: ``make_mlp`` :8-40, ``make_gnn_seq`` :43-106).
+
+The modules built here are ordinary ``torch.nn`` containers so that ``state_dict`` keys and
+shapes equal the reference's (``edge_mlp.0.weight`` ...); they only HOLD parameters — on the
+forward path the math runs in libnlam_b200.so (see ``ops.rowmlp`` / ``FusedMLP``).
+"""
+import torch
+from torch import nn
+
+from . import ops
+
+
+class FusedMLP(nn.Sequential):
+    """``nn.Sequential(Linear, SiLU, ..., Linear[, LayerNorm])`` whose ``forward`` is one
+    fused row-MLP kernel launch.  Under autograd the backward re-evaluates the ATen modules
+    (``ops.RecomputeFn``)."""
+
+    nlam_flags = 0
+
+    def forward(self, x):  # noqa: D102
+        if not x.is_cuda:
+            raise RuntimeError("neural_lam_b200: CUDA tensors only (no CPU fallback)")
+        params = list(self.parameters())
+        names = [n for n, _ in self.named_parameters()]
+
+        def kernel_fn(x_, *_p):
+            return ops.rowmlp(self, [x_], flags=self.nlam_flags)
+
+        def torch_fn(x_, *p_):
+            return _aten_forward(self, dict(zip(names, p_)), x_)
+
+        return ops.run_with_recompute(kernel_fn, torch_fn, [x, *params])
+
+
+def _aten_forward(seq, params, x):
+    """Differentiable ATen evaluation of a make_mlp Sequential with explicit parameter tensors."""
+    h = x
+    for name, mod in seq.named_children():
+        if isinstance(mod, nn.Linear):
+            h = torch.nn.functional.linear(h, params[f"{name}.weight"], params[f"{name}.bias"])
+        elif isinstance(mod, nn.SiLU):
+            h = torch.nn.functional.silu(h)
+        elif isinstance(mod, nn.LayerNorm):
+            h = torch.nn.functional.layer_norm(h, mod.normalized_shape, params[f"{name}.weight"], params[f"{name}.bias"], mod.eps)
+        else:
+            raise TypeError(f"unexpected module {type(mod)} in make_mlp network")
+    return h
+
+
+def make_mlp(blueprint, layer_norm=True):
+    """Widths ``blueprint[0] -> ... -> blueprint[-1]``; SiLU after every Linear but the
+    last; optional trailing LayerNorm (torch defaults)."""
+    n_hidden = len(blueprint) - 2
+    if n_hidden < 0:
+        raise AssertionError("Invalid MLP blueprint")
+    mods = []
+    for k in range(n_hidden + 1):
+        mods.append(nn.Linear(blueprint[k], blueprint[k + 1]))
+        if k < n_hidden:
+            mods.append(nn.SiLU())
+    if layer_norm:
+        mods.append(nn.LayerNorm(blueprint[-1]))
+    return FusedMLP(*mods)
+
+
+class GNNSequential(nn.Module):
+    """Stand-in for ``pyg.nn.Sequential("mesh_rep, edge_rep", [(gnn, "mesh_rep, mesh_rep,
+    edge_rep -> mesh_rep, edge_rep"), ...])`` (reference networks.py:93-106,
+    graph_lam.py:117-126).  Children are named ``module_{i}`` like PyG's so checkpoints map."""
+
+    def __init__(self, gnns):
+        super().__init__()
+        self._n = len(gnns)
+        for i, g in enumerate(gnns):
+            self.add_module(f"module_{i}", g)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        return getattr(self, f"module_{i}")
+
+    def forward(self, mesh_rep, edge_rep):
+        for i in range(self._n):
+            mesh_rep, edge_rep = getattr(self, f"module_{i}")(mesh_rep, mesh_rep, edge_rep)
+        return mesh_rep, edge_rep
+
+
+def make_gnn_seq(edge_index, num_gnn_layers, hidden_layers, hidden_dim, gnn_type="InteractionNet"):
+    """Stack of ``num_gnn_layers`` GNN layers mapping (mesh_rep, edge_rep) -> (mesh_rep, edge_rep)."""
+    from .gnn_layers import get_gnn_class
+
+    if num_gnn_layers < 1:
+        raise ValueError(
+            f"make_gnn_seq requires num_gnn_layers >= 1 (got {num_gnn_layers}); skip the stage for a no-op."
+        )
+    cls = get_gnn_class(gnn_type)
+    return GNNSequential([cls(edge_index, hidden_dim, hidden_layers=hidden_layers) for _ in range(num_gnn_layers)])

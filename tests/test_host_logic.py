@@ -1,0 +1,70 @@
+"""Host-side (CPU) logic of the drop-in layer: reference-compatible structure, index tables."""
+import numpy as np
+import pytest
+import torch
+
+import neural_lam_b200 as nlb
+from neural_lam_b200 import InteractionNet, PropagationNet
+
+
+def _rand_ei(ns, nr, ne, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.stack([torch.randint(0, ns, (ne,), generator=g), torch.randint(0, nr, (ne,), generator=g)])
+    return ei
+
+
+def test_structure_like_reference():
+    # reference tests/test_gnn_layers.py section A (own restatement)
+    assert issubclass(PropagationNet, InteractionNet)
+    ei = _rand_ei(5, 4, 10)
+    assert PropagationNet(ei, 8, aggr="sum").aggr == "mean"
+    assert InteractionNet(ei.clone(), 8, aggr="sum").aggr == "sum"
+    assert InteractionNet(ei.clone(), 8, aggr="mean").aggr == "mean"
+    with pytest.raises(ValueError):
+        InteractionNet(ei, 8, aggr="max")
+    p = PropagationNet(ei, 16)
+    assert p.edge_mlp[0].in_features == 48 and p.aggr_mlp[0].in_features == 32
+    st = p.edge_index
+    assert st[1].min() >= 0 and st[1].max() < p.num_rec and st[0].min() >= p.num_rec
+    assert "edge_index" not in p.state_dict()
+    assert sorted(p.state_dict()) == sorted(
+        [f"{m}.{i}.{w}" for m in ("edge_mlp", "aggr_mlp") for i in (0, 2, 3) for w in ("weight", "bias")]
+    )
+    assert p.state_dict()["edge_mlp.0.weight"].shape == (16, 48)
+    assert p.state_dict()["aggr_mlp.0.weight"].shape == (16, 32)
+
+
+def test_registry():
+    assert set(nlb.GNN_TYPES) == {"InteractionNet", "PropagationNet"}
+    assert nlb.get_gnn_class("PropagationNet") is PropagationNet
+    with pytest.raises(ValueError):
+        nlb.get_gnn_class("nope")
+    with pytest.raises(ValueError):
+        nlb.make_gnn_seq(_rand_ei(4, 4, 8), 0, 1, 8)
+    seq = nlb.make_gnn_seq(_rand_ei(4, 4, 8), 2, 1, 8)
+    assert [n for n, _ in seq.named_children()] == ["module_0", "module_1"]
+
+
+def test_split_mlps_state_dict_names():
+    net = InteractionNet(_rand_ei(6, 4, 12), 8, edge_chunk_sizes=[5, 7], aggr_chunk_sizes=[2, 2])
+    keys = list(net.state_dict())
+    assert "edge_mlp.mlps.1.0.weight" in keys and "aggr_mlp.mlps.0.3.bias" in keys
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_index_tables(seed):
+    ns, nr, ne = 13, 7, 50
+    ei = _rand_ei(ns, nr, ne, seed)
+    net = InteractionNet(ei, 4)
+    snd, rcv = ei[0].numpy(), ei[1].numpy()
+    perm = net._perm32.numpy()
+    assert np.array_equal(perm, np.argsort(rcv, kind="stable"))
+    assert np.array_equal(net._inv_perm32.numpy()[perm], np.arange(ne))
+    rp = net._rowptr32.numpy()
+    assert rp[0] == 0 and rp[-1] == ne
+    for r in range(net.num_rec):
+        assert np.all(rcv[perm[rp[r]:rp[r + 1]]] == r)
+    sp, so = net._sptr32.numpy(), net._sorder32.numpy()
+    for s in range(net.num_send_min):
+        assert np.all(snd[so[sp[s]:sp[s + 1]]] == s)
+    assert net.max_in_degree == np.bincount(rcv).max()
