@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — forecast-steps/sec of the GraphLAM hot path on B200 (contract in the task brief).
+
+Workload (BASELINE.json configs[1]): MEPS-shaped 268x238 grid (xy shape (238,268)), multiscale
+mesh (6 561 nodes, 57 616 m2m / 100 656 g2m / 255 136 m2g edges), GraphLAM hidden_dim=64,
+4 processor layers, fp32 I/O, synthetic inputs (seeded), random-init weights (seed 42).
+
+One "step" = one autoregressive forecast step (StepPredictor.forward + boundary mix) for a
+batch of B independent forecasts on each GPU; value = forecast-steps/sec = N*B*K / t.
+  * `value`     : inputs resident in HBM, the step replayed from a CUDA graph.
+  * `e2e`       : ARForecaster public call path with HOST (pinned) buffers: every step copies that
+                  step's forcing + boundary states host->device and the predicted state
+                  device->host inside the timed region.
+  * `roofline`  : the fused m2m InteractionNet layer (all launches of one nlam_inet_fwd call),
+                  algorithmic bytes / CUDA-event time with L2 flushed between
+                  iterations, against MEASURED_PEAKS.json hbm_gbs.
+  * `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference op sequence
+                  (oracle/reference_port.py) on the host cores, bounded sample.
+N>1: one process per GPU (torchrun), independent replicas (the reference's only parallelism is
+DDP replicas, README.md:486-514): weak scaling, no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GRID = (238, 268)
+HIDDEN = 64
+PROC_LAYERS = 4
+D_STATE, D_FORCING, D_STATIC = 17, 18, 4
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampler for SM clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(device, math="auto"):
+    from neural_lam_b200 import models, synthetic
+
+    spec = synthetic.make_graph_spec(*GRID, hierarchical=False)
+    ds = synthetic.SyntheticDatastore(spec, d_state=D_STATE, d_forcing=D_FORCING, d_static=D_STATIC, boundary_width=10)
+    torch.manual_seed(42)
+    model = models.GraphLAM(ds, spec, hidden_dim=HIDDEN, processor_layers=PROC_LAYERS, math=math)
+    fc = models.ARForecaster(model, ds)
+    if device is not None:
+        fc = fc.to(device)
+    fc.eval()
+    return spec, ds, model, fc
+
+
+def synth_inputs(B, T, G, seed=123, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    init = torch.randn(B, 2, G, D_STATE, generator=g)
+    forc = torch.randn(B, T, G, D_FORCING, generator=g)
+    bnd = torch.randn(B, T, G, D_STATE, generator=g)
+    if pin:
+        init, forc, bnd = init.pin_memory(), forc.pin_memory(), bnd.pin_memory()
+    return init, forc, bnd
+
+
+def oracle_setup(model, fc):
+    from oracle import reference_port as rp  # noqa: F401  (CPU baseline leg only)
+
+    g = {}
+    for k in ("grid_static_features", "g2m_features", "m2g_features", "g2m_edge_index", "m2g_edge_index",
+              "diff_std", "diff_mean", "m2m_features", "m2m_edge_index", "mesh_static_features"):
+        g[k] = getattr(model, k).detach().cpu()
+    g["boundary_mask"] = fc.boundary_mask.detach().cpu()
+    params = {f"predictor.{k}": v.detach().cpu() for k, v in model.state_dict().items()}
+    cfg = dict(model="graph_lam", hidden_layers=1, processor_layers=PROC_LAYERS, mesh_aggr="sum")
+    return params, g, cfg
+
+
+def time_cpu_reference(params, g, cfg, G, steps, warmup, B=1):
+    """The reference op sequence (CPU oracle port: index_select + cat + Linear/SiLU/LayerNorm +
+    index_add_) on all host cores.  Returns (steps/sec, seconds per step, cores)."""
+    from oracle import reference_port as rp
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    init, forc, bnd = synth_inputs(B, max(1, steps + warmup), G)
+    with torch.no_grad():
+        if warmup:
+            rp.ar_rollout(params, g, cfg, init, forc[:, :warmup], bnd[:, :warmup])
+        t0 = time.perf_counter()
+        rp.ar_rollout(params, g, cfg, init, forc[:, warmup:warmup + steps], bnd[:, warmup:warmup + steps])
+        dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps, cores
+
+
+def algorithmic_bytes_inet(B, Ns, Nr, E, H, update_edges, same_nodes):
+    """fp32 forward bytes of one InteractionNet call."""
+    nodes_read = Nr if same_nodes else (Ns + Nr)
+    return (4 * H * B * (nodes_read + E) + 4 * H * B * (Nr + (E if update_edges else 0))
+            + 4 * E + 4 * (Nr + 1) + 4 * (7 * H * H + 8 * H))
+
+
+def roofline_m2m(model, B, device, iters=20):
+    """Time one m2m processor layer (all launches of nlam_inet_fwd) with L2 flushed between
+    iterations; achieved = algorithmic bytes / mean CUDA-event time."""
+    layer = model.processor[0]
+    Nm, E, H = model.num_mesh_nodes, layer.num_edges, HIDDEN
+    g = torch.Generator(device="cpu").manual_seed(7)
+    mesh = torch.randn(B, Nm, H, generator=g).to(device)
+    edge = torch.randn(B, E, H, generator=g).to(device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    with torch.no_grad():
+        for _ in range(3):
+            layer(mesh, mesh, edge)
+        torch.cuda.synchronize(device)
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            layer(mesh, mesh, edge)
+            e.record()
+        torch.cuda.synchronize(device)
+    ms = sorted(s.elapsed_time(e) for s, e in ev)
+    mean_ms = sum(ms) / len(ms)
+    nbytes = algorithmic_bytes_inet(B, Nm, Nm, E, H, True, True)
+    return nbytes, mean_ms, ms[len(ms) // 2]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from neural_lam_b200 import _lib
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    spec, ds, model, fc = build_model(device, math=args.math)
+    G = model.num_grid_nodes
+    T = K + W
+    init, forc, bnd = synth_inputs(B, T, G, seed=123 + rank, pin=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ------------------------------------------------------------------ device-resident value
+    d_init, d_forc, d_bnd = init.to(device), forc.to(device), bnd.to(device)
+    with torch.no_grad():
+        n0 = _lib.lib().nlam_launch_count()
+        bufs = fc.capture(B)
+        # launches of OUR kernels per captured step = those issued during the capture pass
+        n1 = _lib.lib().nlam_launch_count()
+        fc._one_step(bufs)  # eager step to count launches per step exactly
+        launches_per_step = _lib.lib().nlam_launch_count() - n1
+        del n0
+        _, graph, bufs = fc._graph
+
+        def graphed_steps(t0, n):
+            for i in range(t0, t0 + n):
+                bufs["forcing"].copy_(d_forc[:, i])
+                bufs["boundary"].copy_(d_bnd[:, i])
+                graph.replay()
+                bufs["prev_prev"].copy_(bufs["prev"])
+                bufs["prev"].copy_(bufs["out"])
+
+        bufs["prev_prev"].copy_(d_init[:, 0])
+        bufs["prev"].copy_(d_init[:, 1])
+        graphed_steps(0, W)
+        barrier()
+        with ClockSampler(local_rank) as clk:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graphed_steps(W, K)
+            e1.record()
+            barrier()
+            dev_ms = e0.elapsed_time(e1)
+            # keep the sampler alive for at least ~0.5 s of load for short runs
+            if dev_ms < 500:
+                t_end = time.time() + 0.6
+                while time.time() < t_end:
+                    graphed_steps(W, 1)
+                torch.cuda.synchronize(device)
+        clocks = clk.summary()
+
+        # ------------------------------------------------------------------ end-to-end (host buffers)
+        h_out = torch.empty(B, G, D_STATE).pin_memory()
+        stream = torch.cuda.current_stream(device)
+
+        def e2e_steps(t0, n):
+            for i in range(t0, t0 + n):
+                bufs["forcing"].copy_(forc[:, i], non_blocking=True)      # H2D from pinned memory
+                bufs["boundary"].copy_(bnd[:, i], non_blocking=True)     # H2D
+                graph.replay()
+                h_out.copy_(bufs["out"], non_blocking=True)               # D2H of the step result
+                bufs["prev_prev"].copy_(bufs["prev"])
+                bufs["prev"].copy_(bufs["out"])
+            stream.synchronize()
+
+        bufs["prev_prev"].copy_(init[:, 0], non_blocking=True)
+        bufs["prev"].copy_(init[:, 1], non_blocking=True)
+        e2e_steps(0, W)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps(W, K)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        with torch.no_grad():
+            nbytes, mean_ms, med_ms = roofline_m2m(model, B, device)
+        achieved = nbytes / (mean_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            try:
+                traffic = json.load(open(tp)).get("m2m_layer_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = None
+        if world >= 1 and not args.no_cpu_baseline:
+            params, g, cfg = oracle_setup(model, fc)
+            v, sec, cores = time_cpu_reference(params, g, cfg, G, steps=args.cpu_steps, warmup=1, B=1)
+            cpu = {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
+                   "sample": f"B=1, {args.cpu_steps} AR steps of the same GraphLAM config after 1 warm-up "
+                             f"({sec:.3f} s/step, torch CPU {torch.get_num_threads()} threads)"}
+        h2d = B * G * (D_FORCING + D_STATE) * 4
+        d2h = B * G * D_STATE * 4
+        line = {
+            "metric": "forecast-steps/sec (268x238 grid, hidden=64)",
+            "value": world * B * K / (dev_ms * 1e-3),
+            "unit": "forecast-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 I/O; " + ("tf32 tensor-core MLPs, f32 accumulate" if args.math != "fp32" else "f32 FFMA"),
+            "data": "synthetic",
+            "config": {"workload": "MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers "
+                                   "(BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": world * B, "math": args.math,
+                       "parallelism": f"replicas x{world} (independent forecasts per GPU, no collective)",
+                       "l2": "per-step working set (~0.36 GB x B algorithmic) exceeds the 126 MB L2; "
+                             "roofline kernel timed with an explicit 256 MB L2 flush between iterations",
+                       "cuda_graph": True},
+            "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "forecast-steps/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step) * K,
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "m2m InteractionNet layer (nlam_inet_fwd, all launches)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes": nbytes, "ms_mean": mean_ms, "ms_median": med_ms,
+                         "peak_source": peak_src, "l2_flushed": True},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  torch_geometric /
+    pytorch_lightning are not installable here (no network, not in /opt/wheelhouse), so
+    `baseline/_ref` cannot exist; per the tier rules the arm times the CPU oracle port of the
+    reference op sequence (kind "port") on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, ds, model, fc = build_model(None)
+    params, g, cfg = oracle_setup(model, fc)
+    K, W = args.steps, args.warmup
+    k = max(1, min(K, args.cpu_steps))
+    v, sec, cores = time_cpu_reference(params, g, cfg, model.num_grid_nodes, steps=k, warmup=min(W, 1), B=1)
+    line = {
+        "impl": "reference",
+        "metric": "forecast-steps/sec (268x238 grid, hidden=64)",
+        "value": v, "unit": "forecast-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers "
+                               "(BASELINE.json configs[1])", "batch_per_gpu": 1},
+        "cpu_baseline": {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"each step = one B=1 forecast step on the host cores; {k} timed steps "
+                                   f"(bounded from --steps {K})"},
+        "e2e": {"value": v, "unit": "forecast-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="forecasts per GPU per step")
+    ap.add_argument("--math", default="auto", choices=["auto", "tf32", "fp32"])
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,7 @@ extern "C" {
 /* neither math flag: TF32 when the shape is supported by the tensor-core kernels, else FP32 */
 
 #define NLAM_MAX_LINEAR 4
-#define NLAM_MAX_SRC 3
+#define NLAM_MAX_SRC 4
 
 /* One make_mlp network: Linear -> SiLU -> ... -> Linear [-> LayerNorm].
  * w[l] is the nn.Linear weight (out_dim[l], in_dim[l]) row-major, b[l] its bias. */
@@ -89,6 +89,9 @@ typedef struct NlamGraph NlamGraph; /* opaque: receiver-sorted CSR (+ sender CSR
 int nlam_abi_version(void);
 const char* nlam_last_error(void);
 const char* nlam_build_info(void);
+/* number of kernel launches this library has issued in this process (host-side counter; a
+ * launch recorded into a CUDA graph during stream capture counts once) */
+int64_t nlam_launch_count(void);
 
 /* Build the device CSR of one edge set.  edge_index is a HOST pointer to the (2,E) int64
  * array the reference passes to InteractionNet (row 0 senders, row 1 receivers, both

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnlam_b200.so")
 
 NLAM_MAX_LINEAR = 4
-NLAM_MAX_SRC = 3
+NLAM_MAX_SRC = 4
 
 AGGR_MEAN = 0x1
 PROPAGATION = 0x2
@@ -57,6 +57,7 @@ SYMBOLS = {
     "nlam_abi_version": (ctypes.c_int, []),
     "nlam_last_error": (ctypes.c_char_p, []),
     "nlam_build_info": (ctypes.c_char_p, []),
+    "nlam_launch_count": (ctypes.c_int64, []),
     "nlam_graph_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "nlam_graph_destroy": (None, [ctypes.c_void_p]),
     "nlam_graph_num_edges": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -33,6 +33,9 @@ const char* get_error();
     }                                 \
   } while (0)
 
+void count_launch(int n = 1);
+int64_t launch_count();
+
 constexpr int kTileEdges = 128;  // rows of one tensor-core edge tile (UMMA M)
 
 }  // namespace nlam

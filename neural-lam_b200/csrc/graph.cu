@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
 
 #include "common.cuh"
@@ -17,12 +18,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace nlam
 
 using namespace nlam;
 
 extern "C" int nlam_abi_version(void) { return NLAM_ABI_VERSION; }
 extern "C" const char* nlam_last_error(void) { return nlam::get_error(); }
+extern "C" int64_t nlam_launch_count(void) { return nlam::launch_count(); }
 extern "C" const char* nlam_build_info(void) {
   return "libnlam_b200 abi=1 arch=sm_100a cuda=" __DATE__;
 }

@@ -276,6 +276,7 @@ int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
   int occ = std::max<int>(1, (int)((220 * 1024) / (smem + 1024)));
   int grid = (int)std::min<long long>(n_work, (long long)148 * std::min(occ, 4));
   rowmlp_simt_kernel<<<grid, NT, smem, stream>>>(p);
+  count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
@@ -387,6 +388,7 @@ extern "C" int nlam_segment_sum(const int32_t* ptr, const int32_t* order, int64_
     long long total = (long long)B * n_seg * H;
     segment_sum_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(ptr, order, n_seg, x, x_bstride, out, out_bstride, B, H, mean);
   }
+  count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
@@ -406,6 +408,7 @@ extern "C" int nlam_gather_rows(const float* x, int64_t x_bstride, const int32_t
     long long total = (long long)B * n_rows * H;
     gather_rows_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(x, x_bstride, idx, n_rows, out, out_bstride, B, H, deg_ptr);
   }
+  count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
@@ -419,6 +422,7 @@ extern "C" int nlam_step_epilogue(const float* net_out, const float* prev, const
   if (total == 0) return NLAM_OK;
   step_epilogue_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(net_out, prev, boundary, bmask, diff_std,
                                                                                diff_mean, new_state, B, G, D);
+  count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }

@@ -1,0 +1,462 @@
+"""Graph step predictors (GraphLAM / HiLAM) and the autoregressive forecaster with the
+reference's structure, parameter names and forward semantics, running on the B200 kernels.
+
+Reference files mirrored (neural_lam/models/...):
+  step_predictors/base.py        StepPredictor: expand_to_batch :122-139, clamped update :335-396
+  step_predictors/graph/base.py  BaseGraphModel.__init__ :31-178, forward :228-344
+  step_predictors/graph/graph_lam.py     GraphLAM :28-126, process_step :157-188
+  step_predictors/graph/hierarchical.py  BaseHiGraphModel :30-151, process_step :186-292
+  step_predictors/graph/hi_lam.py        HiLAM :114-165, mesh_down_step :167-236,
+                                         mesh_up_step :238-307, hi_processor_step :309-376
+  forecasters/autoregressive.py  ARForecaster.forward :63-149
+
+Differences that do not change results: the datastore argument is any object exposing the
+few quantities the predictors read (``synthetic.SyntheticDatastore``; the xarray/zarr stack
+is out of scope), the graph comes in as a dict of tensors (``synthetic.make_graph_spec`` /
+``synthetic.load_graph``) instead of being read from ``datastore.root_path``, every edge set
+is kept receiver-sorted, and input-independent embeddings are cached between steps while the
+weights do not change.
+"""
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .gnn_layers import InteractionNet, get_gnn_class
+from .networks import GNNSequential, make_mlp
+from .synthetic import normalize_graph
+
+
+def _sort_edges(edge_index, features):
+    """Receiver-sort one edge set (stable), permuting its static features alike."""
+    order = torch.sort(edge_index[1], stable=True).indices
+    if torch.equal(order, torch.arange(order.numel())):
+        return edge_index, features
+    return edge_index[:, order], features[order]
+
+
+class BufferList(nn.Module):
+    """List of non-persistent buffers (reference neural_lam/utils/buffer_list.py:11)."""
+
+    def __init__(self, tensors):
+        super().__init__()
+        self.n = len(tensors)
+        for i, t in enumerate(tensors):
+            self.register_buffer(f"b{i}", t, persistent=False)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [getattr(self, f"b{k}") for k in range(self.n)[i]]
+        if i < 0:
+            i += self.n
+        return getattr(self, f"b{i}")
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return (getattr(self, f"b{i}") for i in range(self.n))
+
+
+class StepPredictor(nn.Module):
+    """One-step predictor ``(X_{t-1}, X_t, forcing_t) -> X_{t+1}`` (reference
+    models/step_predictors/base.py)."""
+
+    def __init__(self, datastore, output_std=False):
+        super().__init__()
+        self.register_buffer("grid_static_features", datastore.grid_static_features.float(), persistent=False)
+        self.num_grid_nodes = self.grid_static_features.shape[0]
+        self.num_state_vars = datastore.num_state_vars
+        self.output_std = bool(output_std)
+        self.grid_output_dim = 2 * self.num_state_vars if self.output_std else self.num_state_vars
+
+    @property
+    def predicts_std(self):
+        return self.output_std
+
+    def expand_to_batch(self, x, batch_size):
+        """(N,d) -> (B,N,d) stride-0 view (reference step_predictors/base.py:122-139)."""
+        return x.unsqueeze(0).expand(batch_size, -1, -1)
+
+    def get_clamped_new_state(self, state_delta, prev_state):
+        """No clamping limits configured -> plain residual update (reference
+        step_predictors/base.py:366 with empty index lists)."""
+        return prev_state + state_delta
+
+
+class BaseGraphModel(StepPredictor):
+    """Encode (g2m) - process (subclass) - decode (m2g) graph model."""
+
+    def __init__(self, datastore, graph, hidden_dim=64, hidden_layers=1, processor_layers=4, mesh_aggr="sum",
+                 output_std=False, g2m_gnn_type="InteractionNet", m2g_gnn_type="InteractionNet", math=None,
+                 **_unused):
+        super().__init__(datastore, output_std=output_std)
+        self.g2m_gnn_type, self.m2g_gnn_type = g2m_gnn_type, m2g_gnn_type
+        self.register_buffer("diff_mean", datastore.state_diff_mean.float(), persistent=False)
+        self.register_buffer("diff_std", datastore.state_diff_std.float(), persistent=False)
+        self.hidden_dim, self.hidden_layers = hidden_dim, hidden_layers
+        self.processor_layers, self.mesh_aggr = processor_layers, mesh_aggr
+        self.math = math
+
+        g = graph if graph.get("normalized") else normalize_graph(graph)
+        self.hierarchical = bool(g["hierarchical"])
+        self._register_graph(g)
+        self.num_mesh_nodes, _ = self.get_num_mesh()
+        self.grid_input_dim = datastore.grid_input_dim
+        self.g2m_edges, g2m_dim = self.g2m_features.shape
+        self.m2g_edges, m2g_dim = self.m2g_features.shape
+
+        self.mlp_blueprint_end = [hidden_dim] * (hidden_layers + 1)
+        self.grid_embedder = make_mlp([self.grid_input_dim] + self.mlp_blueprint_end)
+        self.g2m_embedder = make_mlp([g2m_dim] + self.mlp_blueprint_end)
+        self.m2g_embedder = make_mlp([m2g_dim] + self.mlp_blueprint_end)
+        self.g2m_gnn = get_gnn_class(g2m_gnn_type)(self.g2m_edge_index, hidden_dim, hidden_layers=hidden_layers,
+                                                   update_edges=False, math=math)
+        self.encoding_grid_mlp = make_mlp([hidden_dim] + self.mlp_blueprint_end)
+        self.m2g_gnn = get_gnn_class(m2g_gnn_type)(self.m2g_edge_index, hidden_dim, hidden_layers=hidden_layers,
+                                                   update_edges=False, math=math)
+        self.output_map = make_mlp([hidden_dim] * (hidden_layers + 1) + [self.grid_output_dim], layer_norm=False)
+        self._static_cache = None
+        self._set_mlp_flags()
+
+    # -- graph registration (reference utils/graph.py:425-466: non-persistent buffers) -------
+    def _register_graph(self, g):
+        def reg(name, ei, feat):
+            ei, feat = _sort_edges(ei.long(), feat.float())
+            self.register_buffer(f"{name}_edge_index", ei, persistent=False)
+            self.register_buffer(f"{name}_features", feat, persistent=False)
+
+        reg("g2m", g["g2m_edge_index"], g["g2m_features"])
+        reg("m2g", g["m2g_edge_index"], g["m2g_features"])
+        if self.hierarchical:
+            for name in ("m2m", "mesh_up", "mesh_down"):
+                pairs = [_sort_edges(e.long(), f.float()) for e, f in zip(g[f"{name}_edge_index"], g[f"{name}_features"])]
+                setattr(self, f"{name}_edge_index", BufferList([p[0] for p in pairs]))
+                setattr(self, f"{name}_features", BufferList([p[1] for p in pairs]))
+            self.mesh_static_features = BufferList([m.float() for m in g["mesh_static_features"]])
+        else:
+            reg("m2m", g["m2m_edge_index"], g["m2m_features"])
+            self.register_buffer("mesh_static_features", g["mesh_static_features"].float(), persistent=False)
+
+    def _set_mlp_flags(self):
+        flag = {"auto": 0, None: None, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}[self.math]
+        if flag is None:
+            return
+        for m in self.modules():
+            if hasattr(m, "nlam_flags"):
+                # embedders with tiny inputs always run exact; "tf32" is only forced on the GNNs
+                m.nlam_flags = _lib.MATH_FP32 if self.math == "fp32" else 0
+
+    # -- static (input independent) embeddings ----------------------------------------------
+    def _static_param_version(self):
+        return tuple(p._version for p in self._static_params())
+
+    def _static_params(self):
+        raise NotImplementedError
+
+    def _compute_static(self):
+        raise NotImplementedError
+
+    def static_embeddings(self):
+        """Embeddings of static graph features.  The reference recomputes them every step
+        (graph/base.py:289-295); they only depend on the weights, so in no-grad mode they are
+        cached until a parameter changes."""
+        if torch.is_grad_enabled():
+            return self._compute_static()
+        ver = self._static_param_version()
+        if self._static_cache is None or self._static_cache[0] != ver or self._static_cache[1] != self.diff_std.device:
+            self._static_cache = (ver, self.diff_std.device, self._compute_static())
+        return self._static_cache[2]
+
+    def get_num_mesh(self):
+        raise NotImplementedError
+
+    def process_step(self, mesh_rep, static):
+        raise NotImplementedError
+
+    def forward(self, prev_state, prev_prev_state, forcing):
+        """``(B,G,d_state), (B,G,d_state), (B,G,d_forcing) -> (new_state, pred_std|None)``
+        (reference graph/base.py:228-344)."""
+        B = prev_state.shape[0]
+        # grid feature concat (base.py:275-283) is fused into the embedder kernel
+        grid_emb = self.grid_embedder.apply_rows(
+            [prev_state, prev_prev_state, forcing, self.expand_to_batch(self.grid_static_features, B)])
+        st = self.static_embeddings()
+        mesh_rep = self.g2m_gnn(grid_emb, self.expand_to_batch(st["mesh_emb"], B), self.expand_to_batch(st["g2m_emb"], B))
+        grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)  # base.py:308-310
+        mesh_rep = self.process_step(mesh_rep, st)
+        grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
+        net_output = self.output_map(grid_rep)
+        if self.output_std:
+            pred_delta_mean, pred_std_raw = net_output.chunk(2, dim=-1)
+            pred_std = torch.nn.functional.softplus(pred_std_raw)
+        else:
+            pred_delta_mean, pred_std = net_output, None
+        if not torch.is_grad_enabled() and not self.output_std:
+            # rescale (base.py:339) + residual (base.py:342) in one kernel
+            return ops.step_epilogue(pred_delta_mean, prev_state, None, None, self.diff_std, self.diff_mean), None
+        rescaled = pred_delta_mean * self.diff_std + self.diff_mean
+        return self.get_clamped_new_state(rescaled, prev_state), pred_std
+
+    @torch.no_grad()
+    def forward_with_boundary(self, prev_state, prev_prev_state, forcing, boundary_state, boundary_mask):
+        """Inference step with the ARForecaster boundary mix (autoregressive.py:128-131) fused
+        into the step epilogue kernel."""
+        assert not self.output_std
+        B = prev_state.shape[0]
+        grid_emb = self.grid_embedder.apply_rows(
+            [prev_state, prev_prev_state, forcing, self.expand_to_batch(self.grid_static_features, B)])
+        st = self.static_embeddings()
+        mesh_rep = self.g2m_gnn(grid_emb, self.expand_to_batch(st["mesh_emb"], B), self.expand_to_batch(st["g2m_emb"], B))
+        grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)
+        mesh_rep = self.process_step(mesh_rep, st)
+        grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
+        net_output = self.output_map(grid_rep)
+        return ops.step_epilogue(net_output, prev_state, boundary_state, boundary_mask, self.diff_std, self.diff_mean)
+
+
+class GraphLAM(BaseGraphModel):
+    """Flat (1-level or multiscale) mesh: ``processor_layers`` InteractionNets over m2m."""
+
+    def __init__(self, datastore, graph, hidden_dim=64, hidden_layers=1, processor_layers=4, mesh_aggr="sum",
+                 output_std=False, g2m_gnn_type="InteractionNet", m2g_gnn_type="InteractionNet", math=None,
+                 **kwargs):
+        super().__init__(datastore, graph, hidden_dim=hidden_dim, hidden_layers=hidden_layers,
+                         processor_layers=processor_layers, mesh_aggr=mesh_aggr, output_std=output_std,
+                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math)
+        assert not self.hierarchical, "GraphLAM does not use a hierarchical mesh graph"
+        mesh_dim = self.mesh_static_features.shape[1]
+        m2m_dim = self.m2m_features.shape[1]
+        self.mesh_embedder = make_mlp([mesh_dim] + self.mlp_blueprint_end)
+        self.m2m_embedder = make_mlp([m2m_dim] + self.mlp_blueprint_end)
+        self.processor = GNNSequential([
+            InteractionNet(self.m2m_edge_index, hidden_dim, hidden_layers=hidden_layers, aggr=mesh_aggr, math=math)
+            for _ in range(processor_layers)])
+        self._set_mlp_flags()
+
+    def get_num_mesh(self):
+        return self.mesh_static_features.shape[0], 0
+
+    def _static_params(self):
+        return [p for m in (self.g2m_embedder, self.m2g_embedder, self.mesh_embedder, self.m2m_embedder)
+                for p in m.parameters()]
+
+    def _compute_static(self):
+        return {"g2m_emb": self.g2m_embedder(self.g2m_features), "m2g_emb": self.m2g_embedder(self.m2g_features),
+                "mesh_emb": self.mesh_embedder(self.mesh_static_features),
+                "m2m_emb": self.m2m_embedder(self.m2m_features)}
+
+    def embedd_mesh_nodes(self):
+        return self.mesh_embedder(self.mesh_static_features)
+
+    def process_step(self, mesh_rep, static=None):
+        """reference graph/graph_lam.py:157-188"""
+        static = static or self.static_embeddings()
+        B = mesh_rep.shape[0]
+        mesh_rep, _ = self.processor(mesh_rep, self.expand_to_batch(static["m2m_emb"], B))
+        return mesh_rep
+
+
+class BaseHiGraphModel(BaseGraphModel):
+    """Hierarchical mesh: per-level embedders, mesh-init (up) and read-out (down) GNNs."""
+
+    def __init__(self, datastore, graph, hidden_dim=64, hidden_layers=1, processor_layers=4, mesh_aggr="sum",
+                 output_std=False, g2m_gnn_type="InteractionNet", m2g_gnn_type="InteractionNet",
+                 mesh_up_gnn_type="InteractionNet", mesh_down_gnn_type="InteractionNet", math=None, **kwargs):
+        super().__init__(datastore, graph, hidden_dim=hidden_dim, hidden_layers=hidden_layers,
+                         processor_layers=processor_layers, mesh_aggr=mesh_aggr, output_std=output_std,
+                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math)
+        assert self.hierarchical, "hierarchical models need a hierarchical mesh graph"
+        self.mesh_up_gnn_type, self.mesh_down_gnn_type = mesh_up_gnn_type, mesh_down_gnn_type
+        self.num_levels = len(self.mesh_static_features)
+        self.level_mesh_sizes = [m.shape[0] for m in self.mesh_static_features]
+        mesh_dim = self.mesh_static_features[0].shape[1]
+        same_dim = self.m2m_features[0].shape[1]
+        up_dim = self.mesh_up_features[0].shape[1]
+        down_dim = self.mesh_down_features[0].shape[1]
+        L = self.num_levels
+        end = self.mlp_blueprint_end
+        self.mesh_embedders = nn.ModuleList([make_mlp([mesh_dim] + end) for _ in range(L)])
+        self.mesh_same_embedders = nn.ModuleList([make_mlp([same_dim] + end) for _ in range(L)])
+        self.mesh_up_embedders = nn.ModuleList([make_mlp([up_dim] + end) for _ in range(L - 1)])
+        self.mesh_down_embedders = nn.ModuleList([make_mlp([down_dim] + end) for _ in range(L - 1)])
+        up_cls, down_cls = get_gnn_class(mesh_up_gnn_type), get_gnn_class(mesh_down_gnn_type)
+        self.mesh_init_gnns = nn.ModuleList([
+            up_cls(ei, hidden_dim, hidden_layers=hidden_layers, math=math) for ei in self.mesh_up_edge_index])
+        self.mesh_read_gnns = nn.ModuleList([
+            down_cls(ei, hidden_dim, hidden_layers=hidden_layers, update_edges=False, math=math)
+            for ei in self.mesh_down_edge_index])
+
+    def get_num_mesh(self):
+        n = sum(m.shape[0] for m in self.mesh_static_features)
+        return n, n - self.mesh_static_features[0].shape[0]
+
+    def _static_params(self):
+        mods = [self.g2m_embedder, self.m2g_embedder, *self.mesh_embedders, *self.mesh_same_embedders,
+                *self.mesh_up_embedders, *self.mesh_down_embedders]
+        return [p for m in mods for p in m.parameters()]
+
+    def _compute_static(self):
+        return {
+            "g2m_emb": self.g2m_embedder(self.g2m_features), "m2g_emb": self.m2g_embedder(self.m2g_features),
+            "mesh_emb": self.mesh_embedders[0](self.mesh_static_features[0]),
+            "mesh_levels": [e(f) for e, f in zip(self.mesh_embedders[1:], self.mesh_static_features[1:])],
+            "same": [e(f) for e, f in zip(self.mesh_same_embedders, self.m2m_features)],
+            "up": [e(f) for e, f in zip(self.mesh_up_embedders, self.mesh_up_features)],
+            "down": [e(f) for e, f in zip(self.mesh_down_embedders, self.mesh_down_features)],
+        }
+
+    def embedd_mesh_nodes(self):
+        return self.mesh_embedders[0](self.mesh_static_features[0])
+
+    def process_step(self, mesh_rep, static=None):
+        """reference graph/hierarchical.py:186-292"""
+        static = static or self.static_embeddings()
+        B = mesh_rep.shape[0]
+        ex = lambda t: self.expand_to_batch(t, B)  # noqa: E731
+        levels = [mesh_rep] + [ex(t) for t in static["mesh_levels"]]
+        same = [ex(t) for t in static["same"]]
+        up = [ex(t) for t in static["up"]]
+        down = [ex(t) for t in static["down"]]
+        for l, gnn in enumerate(self.mesh_init_gnns, start=1):
+            levels[l], up[l - 1] = gnn(levels[l - 1], levels[l], up[l - 1])
+        levels, _, _, down = self.hi_processor_step(levels, same, up, down)
+        for l, gnn in zip(range(self.num_levels - 2, -1, -1), reversed(self.mesh_read_gnns)):
+            levels[l] = gnn(levels[l + 1], levels[l], down[l])
+        return levels[0]
+
+    def hi_processor_step(self, mesh_rep_levels, mesh_same_rep, mesh_up_rep, mesh_down_rep):
+        raise NotImplementedError("hi_process_step not implemented")
+
+
+class HiLAM(BaseHiGraphModel):
+    """Hierarchical model with sequential down/up sweeps per processor layer
+    (Hi-LAM, Oskarsson et al. 2023)."""
+
+    def __init__(self, datastore, graph, **kwargs):
+        super().__init__(datastore, graph, **kwargs)
+        P = self.processor_layers
+        self.mesh_down_gnns = nn.ModuleList([self.make_down_gnns() for _ in range(P)])
+        self.mesh_down_same_gnns = nn.ModuleList([self.make_same_gnns() for _ in range(P)])
+        self.mesh_up_gnns = nn.ModuleList([self.make_up_gnns() for _ in range(P)])
+        self.mesh_up_same_gnns = nn.ModuleList([self.make_same_gnns() for _ in range(P)])
+        self._set_mlp_flags()
+
+    def make_same_gnns(self):
+        return nn.ModuleList([InteractionNet(ei, self.hidden_dim, hidden_layers=self.hidden_layers, math=self.math)
+                              for ei in self.m2m_edge_index])
+
+    def make_up_gnns(self):
+        cls = get_gnn_class(self.mesh_up_gnn_type)
+        return nn.ModuleList([cls(ei, self.hidden_dim, hidden_layers=self.hidden_layers, math=self.math)
+                              for ei in self.mesh_up_edge_index])
+
+    def make_down_gnns(self):
+        cls = get_gnn_class(self.mesh_down_gnn_type)
+        return nn.ModuleList([cls(ei, self.hidden_dim, hidden_layers=self.hidden_layers, math=self.math)
+                              for ei in self.mesh_down_edge_index])
+
+    def mesh_down_step(self, levels, same, down, down_gnns, same_gnns):
+        """reference graph/hi_lam.py:205-236"""
+        levels[-1], same[-1] = same_gnns[-1](levels[-1], levels[-1], same[-1])
+        for l, dg, sg in zip(range(self.num_levels - 2, -1, -1), reversed(down_gnns), reversed(same_gnns[:-1])):
+            new_node, down[l] = dg(levels[l + 1], levels[l], down[l])
+            levels[l], same[l] = sg(new_node, new_node, same[l])
+        return levels, same, down
+
+    def mesh_up_step(self, levels, same, up, up_gnns, same_gnns):
+        """reference graph/hi_lam.py:277-307"""
+        levels[0], same[0] = same_gnns[0](levels[0], levels[0], same[0])
+        for l, (ug, sg) in enumerate(zip(up_gnns, same_gnns[1:]), start=1):
+            new_node, up[l - 1] = ug(levels[l - 1], levels[l], up[l - 1])
+            levels[l], same[l] = sg(new_node, new_node, same[l])
+        return levels, same, up
+
+    def hi_processor_step(self, levels, same, up, down):
+        """reference graph/hi_lam.py:350-376"""
+        for dg, dsg, ug, usg in zip(self.mesh_down_gnns, self.mesh_down_same_gnns, self.mesh_up_gnns,
+                                    self.mesh_up_same_gnns):
+            levels, same, down = self.mesh_down_step(levels, same, down, list(dg), list(dsg))
+            levels, same, up = self.mesh_up_step(levels, same, up, list(ug), list(usg))
+        return levels, same, up, down
+
+
+MODELS = {"graph_lam": GraphLAM, "hi_lam": HiLAM}
+
+
+class ARForecaster(nn.Module):
+    """Autoregressive rollout with boundary overwrite (reference
+    models/forecasters/autoregressive.py:63-149).  ``forward`` keeps the reference semantics;
+    ``rollout_graphed`` replays one CUDA-graph-captured forecast step per AR step (inference)."""
+
+    def __init__(self, predictor, datastore):
+        super().__init__()
+        self.predictor = predictor
+        bm = datastore.boundary_mask.float()
+        self.register_buffer("boundary_mask", bm, persistent=False)
+        self.register_buffer("interior_mask", 1.0 - bm, persistent=False)
+        self._graph = None
+
+    @property
+    def predicts_std(self):
+        return self.predictor.predicts_std
+
+    def forward(self, init_states, forcing_features, boundary_states):
+        """init_states (B,2,G,d), forcing (B,T,G,f), boundary (B,T,G,d) -> (prediction (B,T,G,d), std|None)"""
+        prev_prev_state, prev_state = init_states[:, 0], init_states[:, 1]
+        preds, stds = [], []
+        for i in range(forcing_features.shape[1]):
+            pred_state, pred_std = self.predictor(prev_state, prev_prev_state, forcing_features[:, i])
+            new_state = self.boundary_mask * boundary_states[:, i] + self.interior_mask * pred_state
+            preds.append(new_state)
+            if pred_std is not None:
+                stds.append(pred_std)
+            prev_prev_state, prev_state = prev_state, new_state
+        return torch.stack(preds, dim=1), (torch.stack(stds, dim=1) if stds else None)
+
+    # ---- inference fast path: one captured CUDA graph per (B, shapes) ----------------------
+    @torch.no_grad()
+    def capture(self, batch_size):
+        """Capture one forecast step (predictor + boundary mix) into a CUDA graph operating on
+        static buffers.  Returns the dict of static buffers."""
+        p = self.predictor
+        dev = self.boundary_mask.device
+        G, d, f = p.num_grid_nodes, p.num_state_vars, p.grid_input_dim - 2 * p.num_state_vars - p.grid_static_features.shape[1]
+        bufs = {k: torch.zeros(batch_size, G, w, device=dev) for k, w in
+                (("prev", d), ("prev_prev", d), ("forcing", f), ("boundary", d))}
+        p.static_embeddings()  # materialise the weight-only embeddings outside the graph
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm up allocator / lazy handles
+                out = self._one_step(bufs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._one_step(bufs)
+        bufs["out"] = out
+        self._graph = (batch_size, graph, bufs)
+        return bufs
+
+    def _one_step(self, bufs):
+        return self.predictor.forward_with_boundary(bufs["prev"], bufs["prev_prev"], bufs["forcing"],
+                                                    bufs["boundary"], self.boundary_mask)
+
+    @torch.no_grad()
+    def rollout_graphed(self, init_states, forcing_features, boundary_states):
+        """Same result as ``forward`` (no std), replaying the captured step graph."""
+        B, T = forcing_features.shape[0], forcing_features.shape[1]
+        if self._graph is None or self._graph[0] != B:
+            self.capture(B)
+        _, graph, bufs = self._graph
+        out = torch.empty(B, T, *init_states.shape[2:], device=init_states.device)
+        bufs["prev_prev"].copy_(init_states[:, 0])
+        bufs["prev"].copy_(init_states[:, 1])
+        for i in range(T):
+            bufs["forcing"].copy_(forcing_features[:, i])
+            bufs["boundary"].copy_(boundary_states[:, i])
+            graph.replay()
+            out[:, i].copy_(bufs["out"])
+            bufs["prev_prev"].copy_(bufs["prev"])
+            bufs["prev"].copy_(bufs["out"])
+        return out

@@ -19,18 +19,39 @@ class FusedMLP(nn.Sequential):
     nlam_flags = 0
 
     def forward(self, x):  # noqa: D102
-        if not x.is_cuda:
-            raise RuntimeError("neural_lam_b200: CUDA tensors only (no CPU fallback)")
+        return self.apply_rows([x])
+
+    def apply_rows(self, sources, res=None):
+        """``(res or 0) + mlp(cat(sources, -1))`` in ONE kernel: the concatenation of up to 4
+        row-aligned inputs (e.g. prev_state | prev_prev_state | forcing | static features,
+        reference graph/base.py:275-283) and the residual add (base.py:308-310) are fused into
+        the row-MLP kernel instead of being materialised."""
+        for t in sources:
+            if not t.is_cuda:
+                raise RuntimeError("neural_lam_b200: CUDA tensors only (no CPU fallback)")
         params = list(self.parameters())
         names = [n for n, _ in self.named_parameters()]
+        n_src = len(sources)
+        has_res = res is not None
 
-        def kernel_fn(x_, *_p):
-            return ops.rowmlp(self, [x_], flags=self.nlam_flags)
+        def kernel_fn(*args):
+            srcs = list(args[:n_src])
+            r = args[n_src] if has_res else None
+            return ops.rowmlp(self, srcs, res=r, flags=self.nlam_flags)
 
-        def torch_fn(x_, *p_):
-            return _aten_forward(self, dict(zip(names, p_)), x_)
+        def torch_fn(*args):
+            srcs = list(args[:n_src])
+            r = args[n_src] if has_res else None
+            p_ = args[n_src + (1 if has_res else 0):]
+            B = max((t.shape[0] for t in srcs if t.dim() == 3), default=None)
+            if B is not None:
+                srcs = [t if t.dim() == 3 and t.shape[0] == B else (t if t.dim() == 3 else t.unsqueeze(0)).expand(B, -1, -1)
+                        for t in srcs]
+            y = _aten_forward(self, dict(zip(names, p_)), torch.cat(srcs, dim=-1) if n_src > 1 else srcs[0])
+            return y if r is None else r + y
 
-        return ops.run_with_recompute(kernel_fn, torch_fn, [x, *params])
+        tensors = [*sources, *([res] if has_res else []), *params]
+        return ops.run_with_recompute(kernel_fn, torch_fn, tensors)
 
 
 def _aten_forward(seq, params, x):

@@ -303,6 +303,25 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     return rec_out, edge_out, aggr
 
 
+def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean):
+    """new = bmask*boundary + (1-bmask)*(prev + net_out*diff_std + diff_mean) (no-grad path)."""
+    L = _lib.lib()
+    net_out, prev = net_out.contiguous(), prev.contiguous()
+    _require_cuda(net_out, prev, diff_std, diff_mean, boundary, bmask)
+    B, G, D = net_out.shape
+    out = torch.empty_like(net_out)
+    if boundary is not None:
+        boundary, bmask = boundary.contiguous(), bmask.contiguous()
+        assert bmask.numel() == G
+    with torch.cuda.device(net_out.device):
+        _lib.check(L.nlam_step_epilogue(net_out.data_ptr(), prev.data_ptr(),
+                                        boundary.data_ptr() if boundary is not None else None,
+                                        bmask.data_ptr() if boundary is not None else None,
+                                        diff_std.data_ptr(), diff_mean.data_ptr(), out.data_ptr(), B, G, D,
+                                        _stream_ptr(net_out.device)))
+    return out
+
+
 class RecomputeFn(torch.autograd.Function):
     """Forward = hand-written kernels (``kernel_fn``, run without autograd); backward =
     re-evaluate the same math as a differentiable graph (``torch_fn``: custom gather /

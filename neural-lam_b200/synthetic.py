@@ -1,0 +1,256 @@
+"""Synthetic MEPS-shaped graphs and a minimal datastore stand-in.
+
+The reference builds its graphs offline with networkx loops (reference
+neural_lam/create_graph.py:356-862) — far too slow for >=1M-node grids and it needs
+torch_geometric + matplotlib at import.  ``make_graph_spec`` is a vectorised numpy/scipy
+generator that follows the same topology rules on a regular grid:
+
+  * mesh levels: ``nx=3``, ``nlev=int(log(max(Nx,Ny))/log(3))``, ``nleaf=3**nlev``, level
+    ``lev`` has ``n=nleaf/3**lev`` nodes per side (create_graph.py:438-453), positions at cell
+    centres ``linspace(min+d/2, max-d/2, n)`` (:296-303), directed 8-neighbour edges (:306-329)
+    with features ``[len, pos[sender]-pos[receiver]]`` (:135-138, :320-327);
+  * multiscale: coarser levels are merged onto the finest level's nodes at the centre of each
+    3x3 block (:596-611); hierarchical: levels stay separate, up edges = 1-nearest coarser node
+    (:485-509), down edges = reversed with negated offsets (:562-569);
+  * g2m: grid nodes within ``0.67*dm`` of a bottom mesh node, ``dm`` = mesh spacing along the
+    2nd axis (:698-758); m2g: 4 nearest bottom mesh nodes of every grid node (:779-792);
+  * node order: mesh node (i,j) -> i*n+j, grid node (i,j) -> i*Ny+j (sorted labels, :667-676).
+
+``normalize_graph`` applies what ``load_graph`` does at load time (reference
+neural_lam/utils/graph.py:291-303 mesh coords / max grid span, :343-350 edge features /
+longest m2m edge).  Edge ORDER within a set is free in the on-disk format; every edge set is
+stored receiver-sorted here so that the kernels' CSR order is the storage order.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+try:
+    from scipy.spatial import cKDTree
+except Exception:  # pragma: no cover
+    cKDTree = None
+
+
+def _level_positions(xy_min, xy_max, n):
+    d = (xy_max - xy_min) / n
+    lx = np.linspace(xy_min[0] + d[0] / 2, xy_max[0] - d[0] / 2, n)
+    ly = np.linspace(xy_min[1] + d[1] / 2, xy_max[1] - d[1] / 2, n)
+    gx, gy = np.meshgrid(lx, ly, indexing="ij")
+    return np.stack([gx.reshape(-1), gy.reshape(-1)], axis=1)  # node (i,j) -> i*n+j
+
+
+def _grid8_edges(n):
+    """Directed 8-neighbour edges of an n x n lattice, node (i,j) -> i*n+j."""
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    snd, rcv = [], []
+    for di in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            if di == 0 and dj == 0:
+                continue
+            ok = (ii + di >= 0) & (ii + di < n) & (jj + dj >= 0) & (jj + dj < n)
+            snd.append((ii[ok] * n + jj[ok]).reshape(-1))
+            rcv.append(((ii[ok] + di) * n + (jj[ok] + dj)).reshape(-1))
+    return np.concatenate(snd), np.concatenate(rcv)
+
+
+def _edge_features(pos_s, pos_r):
+    vd = pos_s - pos_r
+    ln = np.sqrt((vd ** 2).sum(axis=1, keepdims=True))
+    return np.concatenate([ln, vd], axis=1).astype(np.float32)
+
+
+def _sort_by_receiver(snd, rcv, feat):
+    order = np.lexsort((snd, rcv))  # receiver-major, sender-minor: deterministic
+    return snd[order], rcv[order], feat[order]
+
+
+def _pack(snd, rcv, feat):
+    snd, rcv, feat = _sort_by_receiver(snd, rcv, feat)
+    return torch.from_numpy(np.stack([snd, rcv]).astype(np.int64)), torch.from_numpy(feat)
+
+
+def make_graph_spec(Nx, Ny, hierarchical=False, n_levels=None, spacing=1.0):
+    """Graph tensors (UNNORMALISED, like the files ``create_graph`` writes) for a regular
+    ``Nx x Ny`` grid with unit spacing.  Returns a dict with the keys ``load_graph`` produces
+    plus ``grid_xy`` (G,2), ``grid_shape`` and ``hierarchical``."""
+    if cKDTree is None:  # pragma: no cover
+        raise RuntimeError("scipy is required for the synthetic graph generator")
+    gx, gy = np.meshgrid(np.arange(Nx) * spacing, np.arange(Ny) * spacing, indexing="ij")
+    grid_xy = np.stack([gx.reshape(-1), gy.reshape(-1)], axis=1).astype(np.float64)  # (i,j) -> i*Ny+j
+    xy_min = grid_xy.min(axis=0)
+    xy_max = grid_xy.max(axis=0)
+
+    nlev = int(math.log(max(Nx, Ny)) / math.log(3))
+    nleaf = 3 ** nlev
+    mesh_levels = nlev - 1
+    if n_levels:
+        mesh_levels = min(mesh_levels, n_levels)
+    if mesh_levels < 1:
+        raise ValueError(f"grid {Nx}x{Ny} too small for a mesh")
+    ns = [nleaf // (3 ** lev) for lev in range(1, mesh_levels + 1)]
+    pos = [_level_positions(xy_min, xy_max, n) for n in ns]
+
+    spec = {"hierarchical": bool(hierarchical and mesh_levels > 1), "grid_shape": (Nx, Ny),
+            "grid_xy": torch.from_numpy(grid_xy.astype(np.float32))}
+    if spec["hierarchical"]:
+        m2m_ei, m2m_f = [], []
+        for n, p in zip(ns, pos):
+            s, r = _grid8_edges(n)
+            ei, f = _pack(s, r, _edge_features(p[s], p[r]))
+            m2m_ei.append(ei)
+            m2m_f.append(f)
+        up_ei, up_f, down_ei, down_f = [], [], [], []
+        for l in range(mesh_levels - 1):
+            tree = cKDTree(pos[l + 1])
+            nearest = tree.query(pos[l], 1)[1]
+            s = np.arange(pos[l].shape[0])
+            ei, f = _pack(s, nearest, _edge_features(pos[l][s], pos[l + 1][nearest]))
+            up_ei.append(ei)
+            up_f.append(f)
+            ei, f = _pack(nearest, s, _edge_features(pos[l + 1][nearest], pos[l][s]))
+            down_ei.append(ei)
+            down_f.append(f)
+        spec.update(m2m_edge_index=m2m_ei, m2m_features=m2m_f,
+                    mesh_up_edge_index=up_ei, mesh_up_features=up_f,
+                    mesh_down_edge_index=down_ei, mesh_down_features=down_f,
+                    mesh_static_features=[torch.from_numpy(p.astype(np.float32)) for p in pos])
+    else:
+        n0 = ns[0]
+        snd_all, rcv_all, feat_all = [], [], []
+        for k, (n, p) in enumerate(zip(ns, pos)):
+            s, r = _grid8_edges(n)
+            f = _edge_features(p[s], p[r])
+            # level-k node (a,b) sits on bottom node (3^k a + (3^k-1)/2, same for b)
+            scale = 3 ** k
+            off = (scale - 1) // 2
+
+            def to_bottom(idx, n=n, scale=scale, off=off):
+                a, b = idx // n, idx % n
+                return (a * scale + off) * n0 + (b * scale + off)
+
+            snd_all.append(to_bottom(s))
+            rcv_all.append(to_bottom(r))
+            feat_all.append(f)
+        ei, f = _pack(np.concatenate(snd_all), np.concatenate(rcv_all), np.concatenate(feat_all))
+        spec.update(m2m_edge_index=ei, m2m_features=f,
+                    mesh_up_edge_index=[], mesh_up_features=[], mesh_down_edge_index=[], mesh_down_features=[],
+                    mesh_static_features=torch.from_numpy(pos[0].astype(np.float32)))
+
+    # grid <-> bottom mesh
+    bottom = pos[0]
+    n0 = ns[0]
+    dm = np.sqrt(((bottom[1] - bottom[0]) ** 2).sum())  # nodes (0,1) and (0,0): spacing along 2nd axis
+    gtree = cKDTree(grid_xy)
+    neigh = gtree.query_ball_point(bottom, dm * 0.67)
+    counts = np.fromiter((len(x) for x in neigh), dtype=np.int64, count=len(neigh))
+    g_idx = np.fromiter((i for x in neigh for i in x), dtype=np.int64, count=int(counts.sum()))
+    m_idx = np.repeat(np.arange(bottom.shape[0]), counts)
+    spec["g2m_edge_index"], spec["g2m_features"] = _pack(g_idx, m_idx, _edge_features(grid_xy[g_idx], bottom[m_idx]))
+    mtree = cKDTree(bottom)
+    nn = mtree.query(grid_xy, 4)[1]  # (G,4)
+    g_rep = np.repeat(np.arange(grid_xy.shape[0]), 4)
+    m_flat = nn.reshape(-1)
+    spec["m2g_edge_index"], spec["m2g_features"] = _pack(m_flat, g_rep, _edge_features(bottom[m_flat], grid_xy[g_rep]))
+    return spec
+
+
+def normalize_graph(spec):
+    """What ``load_graph`` does to the on-disk tensors (reference utils/graph.py:291-303,
+    :343-350): mesh coordinates / max grid span, edge features / longest m2m edge."""
+    out = dict(spec)
+    gxy = spec["grid_xy"]
+    span = float(max(gxy[:, 0].max() - gxy[:, 0].min(), gxy[:, 1].max() - gxy[:, 1].min()))
+    span = span if span != 0 else 1.0
+    hier = spec["hierarchical"]
+    m2m_f = spec["m2m_features"] if hier else [spec["m2m_features"]]
+    longest = max(float(f[:, 0].max()) for f in m2m_f)
+    if hier:
+        out["mesh_static_features"] = [m / span for m in spec["mesh_static_features"]]
+        for k in ("m2m_features", "mesh_up_features", "mesh_down_features"):
+            out[k] = [f / longest for f in spec[k]]
+    else:
+        out["mesh_static_features"] = spec["mesh_static_features"] / span
+        out["m2m_features"] = spec["m2m_features"] / longest
+    out["g2m_features"] = spec["g2m_features"] / longest
+    out["m2g_features"] = spec["m2g_features"] / longest
+    out["normalized"] = True
+    return out
+
+
+def save_graph(spec, graph_dir):
+    """Write the reference's on-disk format (docs/graph_storage_spec.md; file set as in
+    create_graph.py:366-410): lists per level for m2m / mesh / up / down."""
+    os.makedirs(graph_dir, exist_ok=True)
+    hier = spec["hierarchical"]
+    as_list = (lambda v: v) if hier else (lambda v: [v])
+    torch.save(as_list(spec["m2m_edge_index"]), os.path.join(graph_dir, "m2m_edge_index.pt"))
+    torch.save(as_list(spec["m2m_features"]), os.path.join(graph_dir, "m2m_features.pt"))
+    torch.save(as_list(spec["mesh_static_features"]), os.path.join(graph_dir, "mesh_features.pt"))
+    for k in ("g2m", "m2g"):
+        torch.save(spec[f"{k}_edge_index"], os.path.join(graph_dir, f"{k}_edge_index.pt"))
+        torch.save(spec[f"{k}_features"], os.path.join(graph_dir, f"{k}_features.pt"))
+    if hier:
+        for k in ("mesh_up", "mesh_down"):
+            torch.save(spec[f"{k}_edge_index"], os.path.join(graph_dir, f"{k}_edge_index.pt"))
+            torch.save(spec[f"{k}_features"], os.path.join(graph_dir, f"{k}_features.pt"))
+    with open(os.path.join(graph_dir, "metainfo.yaml"), "w", encoding="utf-8") as f:
+        f.write("spec_version: '1.0'\n")
+
+
+def load_graph(graph_dir, grid_xy):
+    """Read a graph directory in the reference's current on-disk format (the file set
+    ``load_graph`` reads, reference utils/graph.py:146-422) into an unnormalised spec."""
+    def ld(fn):
+        return torch.load(os.path.join(graph_dir, fn), map_location="cpu", weights_only=True)
+
+    m2m_ei = ld("m2m_edge_index.pt")
+    hier = len(m2m_ei) > 1
+    spec = {"hierarchical": hier, "grid_xy": torch.as_tensor(grid_xy, dtype=torch.float32).reshape(-1, 2),
+            "g2m_edge_index": ld("g2m_edge_index.pt"), "m2g_edge_index": ld("m2g_edge_index.pt"),
+            "g2m_features": ld("g2m_features.pt"), "m2g_features": ld("m2g_features.pt")}
+    m2m_f, mesh_f = ld("m2m_features.pt"), ld("mesh_features.pt")
+    if hier:
+        spec.update(m2m_edge_index=list(m2m_ei), m2m_features=list(m2m_f), mesh_static_features=list(mesh_f),
+                    mesh_up_edge_index=list(ld("mesh_up_edge_index.pt")), mesh_up_features=list(ld("mesh_up_features.pt")),
+                    mesh_down_edge_index=list(ld("mesh_down_edge_index.pt")),
+                    mesh_down_features=list(ld("mesh_down_features.pt")))
+    else:
+        spec.update(m2m_edge_index=m2m_ei[0], m2m_features=m2m_f[0], mesh_static_features=mesh_f[0],
+                    mesh_up_edge_index=[], mesh_up_features=[], mesh_down_edge_index=[], mesh_down_features=[])
+    return spec
+
+
+class SyntheticDatastore:
+    """The handful of quantities the graph step predictors read from a reference
+    ``BaseDatastore`` (models/step_predictors/base.py:60-106, graph/base.py:86-135), filled
+    with synthetic values of the right shape: static grid features
+    ~N(0,1) (seed 123), one-step difference statistics mean 0 / std 1, rectangular boundary
+    frame."""
+
+    def __init__(self, spec, d_state=17, d_forcing=18, d_static=4, boundary_width=10, seed=123):
+        Nx, Ny = spec["grid_shape"]
+        self.grid_shape = (Nx, Ny)
+        self.num_grid_nodes = Nx * Ny
+        self.num_state_vars = d_state
+        self.num_forcing_vars = d_forcing  # already includes the past/future window
+        self.num_static_vars = d_static
+        g = torch.Generator().manual_seed(seed)
+        self.grid_static_features = torch.randn(self.num_grid_nodes, d_static, generator=g)
+        self.state_diff_mean = torch.zeros(d_state)
+        self.state_diff_std = torch.ones(d_state)
+        m = torch.zeros(Nx, Ny)
+        w = min(boundary_width, max(1, min(Nx, Ny) // 4))
+        m[:w, :] = 1
+        m[-w:, :] = 1
+        m[:, :w] = 1
+        m[:, -w:] = 1
+        self.boundary_mask = m.reshape(-1, 1)
+        gxy = spec["grid_xy"]
+        self.grid_xy_max_span = float(max(gxy[:, 0].max() - gxy[:, 0].min(), gxy[:, 1].max() - gxy[:, 1].min()))
+
+    @property
+    def grid_input_dim(self):
+        # reference utils/graph.py:507-512: 2*state + static + forcing window
+        return 2 * self.num_state_vars + self.num_static_vars + self.num_forcing_vars
