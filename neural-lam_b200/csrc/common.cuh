@@ -59,6 +59,7 @@ struct NlamGraph {
   // [rowptr[tile_rec[t]], rowptr[tile_rec[t+1]]).  n_tiles == 0 if some in-degree > 128.
   int32_t n_tiles = 0;
   int32_t* tile_rec = nullptr;  // n_tiles+1
+  int32_t* tile_e0 = nullptr;   // n_tiles+1: first CSR edge of each tile
   std::vector<int32_t> h_tile_rec, h_rowptr;
 };
 

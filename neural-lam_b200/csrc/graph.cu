@@ -106,6 +106,8 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
     }
     g->n_tiles = (int32_t)tile_rec.size() - 1;
   }
+  std::vector<int32_t> tile_e0(tile_rec.size());
+  for (size_t i = 0; i < tile_rec.size(); ++i) tile_e0[i] = rowptr[tile_rec[i]];
   g->h_tile_rec = tile_rec;
   g->h_rowptr = rowptr;
 
@@ -126,7 +128,7 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
   if ((rc = upload(&g->rowptr, rowptr)) || (rc = upload(&g->src, src)) || (rc = upload(&g->dst, dst)) ||
       (rc = upload(&g->perm, perm)) || (rc = upload(&g->inv_perm, inv_perm)) ||
       (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
-      (rc = upload(&g->tile_rec, tile_rec))) {
+      (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0))) {
     cudaSetDevice(prev_dev);
     nlam_graph_destroy(g);
     return rc;
@@ -149,6 +151,7 @@ extern "C" void nlam_graph_destroy(NlamGraph* g) {
   cudaFree(g->sptr);
   cudaFree(g->sperm);
   cudaFree(g->tile_rec);
+  cudaFree(g->tile_e0);
   cudaSetDevice(prev);
   delete g;
 }

@@ -1,8 +1,826 @@
-// placeholder: tcgen05 kernels not built yet
+// tcgen05 / TMEM / TMA kernels (sm_100a) for hidden width H = 64, TF32 inputs, fp32 accumulate.
+//
+// One persistent, warp-specialised kernel `tc_mlp_kernel` evaluates, per 128-row tile,
+//     y = [LayerNorm]( W2 · SiLU(W1 · a + b1) + b2 )            (make_mlp, networks.py:27-40)
+// with the two Linear layers as tcgen05.mma (kind::tf32, M=128, N=64|32, accumulators in
+// TMEM) and everything around them fused:
+//   edge mode (InteractionNet message + aggregate, gnn_layers.py:144-189):
+//     a = [e | x[src] | x[dst]] : e tile by TMA, sender/receiver rows gathered with cp.async
+//     straight into the swizzled UMMA operand layout; epilogue adds the edge residual
+//     (e' = e + m, coalesced store) and segment-sums m over the CSR receiver segments of the
+//     tile (tiles hold whole receivers, so no atomics and a deterministic order).
+//   row mode (node update gnn_layers.py:148-151, embedders / grid MLPs base.py:286-322):
+//     a = up to two 64-wide row blocks by TMA (e.g. [rec | aggr]) or a generic concatenation
+//     of narrow inputs (grid features 17|17|18|4); optional residual, optional LayerNorm.
+//
+// Warp roles (448 threads, 1 CTA / SM, persistent over (batch, tile) work items):
+//   warps 0-7   epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/SiLU/LayerNorm/residual,
+//               segmented reduction, coalesced stores.  warp%4 selects the TMEM lane quarter,
+//               warp/4 the column half.
+//   warps 8-11  producers: index-driven gathers (cp.async 16 B, manual 128B swizzle)
+//   warp 12     TMEM allocation + single-thread tcgen05.mma issue
+//   warp 13     TMA loads (weights once, A tiles per work item)
+//
+// Shared memory (dynamic, 1024-byte aligned): W1 6x8 KB | W2 2x8 KB | A 8x16 KB | HB 2x16 KB |
+// barriers + LayerNorm exchange + local CSR offsets = 227 KB.  TMA-loaded A blocks are double
+// buffered (edge mode: e tile stage 0 = blocks 0-1, stage 1 = blocks 6-7, gathered sender /
+// receiver rows = blocks 2-5; row mode: stage s = blocks [s*nb1, (s+1)*nb1)), and so are the
+// TMEM accumulators (D1/D2 of stage s at columns s*128 / s*128+64), so that the TMA loads, the
+// gathers and the first GEMM of tile i+1 overlap the epilogue of tile i.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
+
 namespace nlam {
-bool tc_rowmlp_supported(const NlamMlp*, const NlamRowSrc*, int, const NlamRowSrc*, const NlamRowSrc*, int64_t) { return false; }
-int tc_rowmlp(const NlamMlp*, const NlamRowSrc*, int, const NlamRowSrc*, float*, int64_t, int, cudaStream_t) { set_error("tc_rowmlp: not built"); return NLAM_E_UNSUPPORTED; }
-bool tc_edge_supported(const NlamGraph*, const NlamMlp*, int) { return false; }
-int tc_edge(const NlamGraph*, const NlamMlp*, const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, float*, int, int, cudaStream_t) { set_error("tc_edge: not built"); return NLAM_E_UNSUPPORTED; }
+
+constexpr int TC_THREADS = 448;
+constexpr int EPI_THREADS = 256;
+constexpr int PROD_THREADS = 128;
+constexpr int BM = 128;
+constexpr uint32_t A_BLOCK = 16384;  // 128 rows x 128 B
+constexpr uint32_t W_BLOCK = 8192;   // 64 rows x 128 B
+constexpr uint32_t OFF_W1 = 0;
+constexpr uint32_t OFF_W2 = 6 * W_BLOCK;
+constexpr uint32_t OFF_A = 8 * W_BLOCK;
+constexpr uint32_t OFF_HB = OFF_A + 8 * A_BLOCK;
+constexpr uint32_t OFF_MISC = OFF_HB + 2 * A_BLOCK;
+constexpr uint32_t MISC_BYTES = 3072;  // total = 232448 B = the 227 KB opt-in maximum
+constexpr uint32_t TC_SMEM = OFF_MISC + MISC_BYTES;
+
+struct TcParams {
+  int mode_edge;
+  int nb1;        // K blocks (32 floats each) of the first Linear's input
+  int a0_blocks;  // blocks loaded by TMA from source 0 / source 1
+  int a1_blocks;
+  int a0_batched, a1_batched;
+  // gather sources (edge mode): blocks [2,4) <- gsrc[0][gidx[0][row]], [4,6) <- gsrc[1][..]
+  const float* gsrc[2];
+  long long gbs[2];
+  const int32_t* gidx[2];
+  // generic element-wise sources (row mode): concatenated into blocks [0, nb1)
+  int n_elem;
+  const float* esrc[NLAM_MAX_SRC];
+  long long ebs[NLAM_MAX_SRC];
+  int edim[NLAM_MAX_SRC];
+  int k_real;
+  const float* b1;
+  const float* b2;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int n2;    // padded N of the second Linear (64 or 32)
+  int nout;  // real output width
+  int res_block;  // first A block holding the residual rows, or -1
+  float* out;     // (B, n_rows, nout) dense; NULL in edge mode without edge update
+  float* aggr;    // edge mode: (B, n_rec, 64)
+  int mean;
+  long long n_rows;
+  int B;
+  int n_tiles;
+  const int32_t* tile_rec;
+  const int32_t* tile_e0;  // first CSR edge of each tile (n_tiles+1)
+  const int32_t* rowptr;
+  long long n_rec;
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) {  // bounded: a protocol bug must not hang the GPU
+      printf("nlam tc kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;      // SBO
+  d |= (uint64_t)1 << 46;                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)   (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// byte offset of 16-byte chunk `ch` (0..7) of row `row` inside a 128B-swizzled [128][32 float] block
+__device__ __forceinline__ uint32_t swz(int row, int ch) { return (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4)); }
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  // misc region: mbarriers | tmem ptr | LayerNorm exchange | local CSR offsets
+  const uint32_t mb = sbase + OFF_MISC;
+  const uint32_t bar_w = mb + 0;
+  const uint32_t bar_a_gat_full = mb + 8;
+  const uint32_t bar_a_free_g = mb + 16;
+  const uint32_t bar_hb_full = mb + 24;
+  // stage-indexed (add 8*s)
+  const uint32_t bar_a_tma_full = mb + 32;
+  const uint32_t bar_epi_done = mb + 48;
+  const uint32_t bar_d1_full = mb + 64;
+  const uint32_t bar_d2_full = mb + 80;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 96);
+  float* ln_x = reinterpret_cast<float*>(smem + OFF_MISC + 128);   // [2 stats][2 halves][128 rows]
+  int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 128 + 2048);  // local CSR offsets, <= 129 entries
+
+  if ((sbase & 1023u) != 0) {
+    if (tid == 0) printf("nlam tc kernel: dynamic shared memory not 1024-byte aligned\n");
+    __trap();
+  }
+
+  const bool has_tma_a = (p.a0_blocks + p.a1_blocks) > 0;
+  const bool has_prod = p.mode_edge || p.n_elem > 0;
+
+  if (warp == 12) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1);
+      mbar_init(bar_a_gat_full, PROD_THREADS);
+      mbar_init(bar_a_free_g, 1);
+      mbar_init(bar_hb_full, EPI_THREADS);
+      for (int st = 0; st < 2; ++st) {
+        mbar_init(bar_a_tma_full + 8 * st, 1);
+        mbar_init(bar_epi_done + 8 * st, 1);
+        mbar_init(bar_d1_full + 8 * st, 1);
+        mbar_init(bar_d2_full + 8 * st, 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 13 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    if (p.a0_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    if (p.a1_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // first A block of TMA stage st (edge mode keeps the gathered blocks 2-5 single buffered)
+  const int stage_blk1 = p.mode_edge ? 6 : p.nb1;
+
+  const long long n_work = (long long)p.n_tiles * p.B;
+
+  if (warp == 13) {
+    // =============================== TMA loader ===============================
+    if (lane == 0) {
+      const uint32_t w2_block_bytes = (uint32_t)p.n2 * 128u;
+      mbar_expect_tx(bar_w, (uint32_t)p.nb1 * W_BLOCK + 2u * w2_block_bytes);
+      for (int j = 0; j < p.nb1; ++j) tma_load_2d(sbase + OFF_W1 + j * W_BLOCK, &tmW1, bar_w, 32 * j, 0);
+      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * W_BLOCK, &tmW2, bar_w, 32 * j, 0);
+      if (has_tma_a) {
+        int it = 0;
+        for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+          const int b = (int)(w / p.n_tiles);
+          const int t = (int)(w - (long long)b * p.n_tiles);
+          const int st = it & 1;
+          const int row0 = p.mode_edge ? p.tile_e0[t] : t * BM;
+          const uint32_t abase = sbase + OFF_A + (st ? stage_blk1 : 0) * A_BLOCK;
+          const uint32_t full = bar_a_tma_full + 8 * st;
+          mbar_wait(bar_epi_done + 8 * st, (uint32_t)(((it >> 1) & 1) ^ 1));  // tile it-2 released the stage
+          mbar_expect_tx(full, (uint32_t)(p.a0_blocks + p.a1_blocks) * A_BLOCK);
+          for (int j = 0; j < p.a0_blocks; ++j)
+            tma_load_3d(abase + j * A_BLOCK, &tmA0, full, 32 * j, row0, p.a0_batched ? b : 0);
+          for (int j = 0; j < p.a1_blocks; ++j)
+            tma_load_3d(abase + (p.a0_blocks + j) * A_BLOCK, &tmA1, full, 32 * j, row0, p.a1_batched ? b : 0);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // =============================== MMA issuer ===============================
+    // Software pipelined: GEMM1 of tile i+1 is issued as soon as its operands have landed,
+    // GEMM2 of tile i as soon as the epilogue has produced the hidden activations.
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_tf32(BM, 64);
+      const uint32_t idesc2 = umma_idesc_tf32(BM, p.n2);
+      int n_my = 0;
+      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
+      mbar_wait(bar_w, 0);
+      int g1 = 0, g2 = 0;
+      uint32_t idle = 0;
+      while (g2 < n_my) {
+        bool progress = false;
+        if (g1 < n_my && g1 <= g2 + 1) {
+          const int it = g1, st = it & 1;
+          const uint32_t sph = (uint32_t)((it >> 1) & 1);
+          bool ready = true;
+          if (has_tma_a) ready = mbar_test(bar_a_tma_full + 8 * st, sph);
+          else ready = mbar_test(bar_epi_done + 8 * st, sph ^ 1);  // accumulators of tile it-2 drained
+          if (ready && has_prod) ready = mbar_test(bar_a_gat_full, (uint32_t)(it & 1));
+          if (ready) {
+            tc_fence_after();
+            const uint32_t d1 = tmem_base + st * 128;
+            for (int j = 0; j < p.nb1; ++j) {
+              // A block j: TMA blocks come from the stage, produced blocks (edge gathers) are fixed
+              int blk;
+              if (p.mode_edge) blk = (j < 2) ? (st ? 6 + j : j) : j;
+              else blk = has_tma_a ? (st ? stage_blk1 : 0) + j : j;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t ad = umma_desc(sbase + OFF_A + blk * A_BLOCK + k * 32);
+                uint64_t bd = umma_desc(sbase + OFF_W1 + j * W_BLOCK + k * 32);
+                umma_tf32(d1, ad, bd, idesc1, (uint32_t)((j | k) != 0));
+              }
+            }
+            umma_commit(bar_d1_full + 8 * st);
+            if (has_prod) umma_commit(bar_a_free_g);
+            ++g1;
+            progress = true;
+          }
+        }
+        if (g2 < g1) {
+          const int it = g2, st = it & 1;
+          if (mbar_test(bar_hb_full, (uint32_t)(it & 1))) {
+            tc_fence_after();
+            const uint32_t d2 = tmem_base + st * 128 + 64;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t ad = umma_desc(sbase + OFF_HB + j * A_BLOCK + k * 32);
+                uint64_t bd = umma_desc(sbase + OFF_W2 + j * W_BLOCK + k * 32);
+                umma_tf32(d2, ad, bd, idesc2, (uint32_t)((j | k) != 0));
+              }
+            }
+            umma_commit(bar_d2_full + 8 * st);
+            ++g2;
+            progress = true;
+          }
+        }
+        if (progress) idle = 0;
+        else if (++idle > (1u << 26)) {
+          printf("nlam tc kernel: MMA issuer timeout (block %d g1 %d g2 %d)\n", blockIdx.x, g1, g2);
+          __trap();
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // =============================== producers ===============================
+    if (has_prod) {
+      const int pt = tid - 8 * 32;  // 0..127
+      int it = 0;
+      for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int b = (int)(w / p.n_tiles);
+        const int t = (int)(w - (long long)b * p.n_tiles);
+        mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
+        if (p.mode_edge) {
+          const int e0 = p.tile_e0[t];
+          const int ne = p.tile_e0[t + 1] - e0;
+          // each warp owns 32 tile rows; a half-warp copies one 256-byte row per instruction
+          const int pw = pt >> 5;
+          const int my_row = pw * 32 + lane;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            int my_idx = 0;
+            if (my_row < ne) my_idx = p.gidx[s][e0 + my_row];
+            const float* base = p.gsrc[s] + (long long)b * p.gbs[s];
+            const uint32_t blk0 = sbase + OFF_A + (2 + 2 * s) * A_BLOCK;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const int rl = 2 * i + (lane >> 4);  // row within the warp's 32
+              const int row = pw * 32 + rl;
+              const int src_row = __shfl_sync(0xffffffffu, my_idx, rl);
+              const int ch = lane & 15;  // 16-byte chunk of the 256-byte row
+              const float* g = base + (long long)src_row * 64 + ch * 4;
+              const uint32_t dst = blk0 + (ch >> 3) * A_BLOCK + swz(row, ch & 7);
+              if (row < ne) cp_async_16(dst, g);
+            }
+          }
+          cp_async_wait_all();
+        } else {
+          // generic concatenation of narrow inputs: element-wise, zero padded to nb1*32 columns
+          const int kpad = p.nb1 * 32;
+          const long long row0 = (long long)t * BM;
+          for (int i = pt; i < BM * kpad; i += PROD_THREADS) {
+            const int row = i / kpad, col = i - row * kpad;
+            float v = 0.f;
+            const long long gr = row0 + row;
+            if (gr < p.n_rows && col < p.k_real) {
+              int c = col;
+#pragma unroll
+              for (int s = 0; s < NLAM_MAX_SRC; ++s) {
+                if (s < p.n_elem) {
+                  if (c >= 0 && c < p.edim[s]) v = p.esrc[s][(long long)b * p.ebs[s] + gr * p.edim[s] + c];
+                  c -= p.edim[s];
+                }
+              }
+            }
+            const uint32_t off = OFF_A + (col >> 5) * A_BLOCK + swz(row, (col & 31) >> 2) + (col & 3) * 4;
+            *reinterpret_cast<float*>(smem + off) = v;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_a_gat_full);
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-7) ===============================
+    const int q = warp & 3;        // TMEM lane quarter
+    const int half = warp >> 2;    // column half
+    const int row = q * 32 + lane;  // tile row owned by this thread
+    const int c0 = half * 32;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    int it = 0;
+    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int st = it & 1;
+      const uint32_t sph = (uint32_t)((it >> 1) & 1);
+      const uint32_t tmem_d1 = tmem_base + st * 128;
+      const uint32_t tmem_d2 = tmem_d1 + 64;
+      const int b = (int)(w / p.n_tiles);
+      const int t = (int)(w - (long long)b * p.n_tiles);
+      long long row0;
+      int nrows, r0 = 0, nrec = 0;
+      if (p.mode_edge) {
+        r0 = p.tile_rec[t];
+        nrec = p.tile_rec[t + 1] - r0;
+        const int e0 = p.tile_e0[t];
+        row0 = e0;
+        nrows = p.tile_e0[t + 1] - e0;
+        if (tid <= nrec) lp[tid] = p.rowptr[r0 + tid] - e0;
+      } else {
+        row0 = (long long)t * BM;
+        nrows = (int)min((long long)BM, p.n_rows - row0);
+      }
+
+      // ---- E1: hidden = SiLU(D1 + b1) -> HB (UMMA A operand layout) ----
+      mbar_wait(bar_d1_full + 8 * st, sph);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_d1 + t_lane + c0, v);
+      {
+        uint8_t* hb = smem + OFF_HB + half * A_BLOCK;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 o;
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c0 + 4 * k));
+          o.x = silu_fast(v[4 * k + 0] + bb.x);
+          o.y = silu_fast(v[4 * k + 1] + bb.y);
+          o.z = silu_fast(v[4 * k + 2] + bb.z);
+          o.w = silu_fast(v[4 * k + 3] + bb.w);
+          *reinterpret_cast<float4*>(hb + swz(row, k)) = o;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_hb_full);
+
+      // ---- E2: y = D2 + b2, LayerNorm, residual ----
+      mbar_wait(bar_d2_full + 8 * st, sph);
+      tc_fence_after();
+      const bool active = c0 < p.n2;
+      if (active) tmem_ld32(tmem_d2 + t_lane + c0, v);
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (c0 + 4 * k < p.nout) {  // nout is a multiple of 4 when it is 64; ragged (17) handled per element
+            const float* b2p = p.b2 + c0 + 4 * k;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (c0 + 4 * k + i < p.nout) v[4 * k + i] += __ldg(b2p + i);
+          }
+        }
+      }
+      if (p.gamma) {
+        // two-pass LayerNorm over 64 columns split across the two column halves
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s += v[i];
+        ln_x[half * BM + row] = s;
+        named_bar_sync(1, EPI_THREADS);
+        const float mu = (ln_x[row] + ln_x[BM + row]) * (1.0f / 64.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] -= mu;
+          sq += v[i] * v[i];
+        }
+        ln_x[2 * BM + half * BM + row] = sq;
+        named_bar_sync(1, EPI_THREADS);
+        const float var = (ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
+        const float rstd = rsqrtf(var + p.eps);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4 * k));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * k));
+          v[4 * k + 0] = v[4 * k + 0] * rstd * g4.x + b4.x;
+          v[4 * k + 1] = v[4 * k + 1] * rstd * g4.y + b4.y;
+          v[4 * k + 2] = v[4 * k + 2] * rstd * g4.z + b4.z;
+          v[4 * k + 3] = v[4 * k + 3] * rstd * g4.w + b4.w;
+        }
+      }
+
+      // staging: messages (edge mode) -> HB; output rows -> residual blocks in place, or HB
+      const bool wide = (p.nout == 64);
+      uint8_t* stage = nullptr;  // where the 64-wide output tile is staged (swizzled block pair)
+      if (wide) {
+        if (p.mode_edge) {
+          uint8_t* hb = smem + OFF_HB + half * A_BLOCK;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(hb + swz(row, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+        if (p.res_block >= 0) {
+          if (has_tma_a) mbar_wait(bar_a_tma_full + 8 * st, sph);  // TMA-written rows visible to this thread
+          stage = smem + OFF_A + ((st ? stage_blk1 : 0) + p.res_block) * A_BLOCK;
+          if (p.out) {
+            uint8_t* rb = stage + half * A_BLOCK;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float4* ptr = reinterpret_cast<float4*>(rb + swz(row, k));
+              float4 r = *ptr;
+              r.x += v[4 * k];
+              r.y += v[4 * k + 1];
+              r.z += v[4 * k + 2];
+              r.w += v[4 * k + 3];
+              *ptr = r;
+            }
+          }
+        } else if (!p.mode_edge) {
+          stage = smem + OFF_HB;
+          uint8_t* hb = stage + half * A_BLOCK;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(hb + swz(row, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+      } else if (active) {
+        // narrow output (e.g. output_map 64 -> 17): plain [128][nout] floats in HB, odd pitch
+        float* flat = reinterpret_cast<float*>(smem + OFF_HB);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.nout) flat[row * p.nout + c0 + i] = v[i];
+      }
+      named_bar_sync(1, EPI_THREADS);
+
+      // ---- coalesced copy-out ----
+      if (p.out) {
+        if (wide && stage) {
+          float* og = p.out + ((long long)b * p.n_rows + row0) * 64;
+          for (int i = tid; i < nrows * 16; i += EPI_THREADS) {
+            const int r = i >> 4, ch = i & 15;
+            const float4 val = *reinterpret_cast<const float4*>(stage + (ch >> 3) * A_BLOCK + swz(r, ch & 7));
+            *reinterpret_cast<float4*>(og + (long long)r * 64 + ch * 4) = val;
+          }
+        } else if (!wide) {
+          const float* flat = reinterpret_cast<const float*>(smem + OFF_HB);
+          float* og = p.out + ((long long)b * p.n_rows + row0) * p.nout;
+          const int n = nrows * p.nout;
+          for (int i = tid; i < n; i += EPI_THREADS) og[i] = flat[i];
+        }
+      }
+      // ---- segmented sum of the messages over the tile's receivers (CSR order) ----
+      if (p.mode_edge) {
+        // thread = (float4 column group cg, receiver group g): 16 x 16
+        const int cg = tid & 15, g = tid >> 4;
+        const uint8_t* mbase = smem + OFF_HB + (cg >> 3) * A_BLOCK;
+        const int chq = cg & 7;
+        for (int j = g; j < nrec; j += 16) {
+          const int k0 = lp[j], k1 = lp[j + 1];
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = k0; k < k1; ++k) {
+            const float4 m4 = *reinterpret_cast<const float4*>(mbase + swz(k, chq));
+            acc.x += m4.x; acc.y += m4.y; acc.z += m4.z; acc.w += m4.w;
+          }
+          if (p.mean) {
+            const float sc = 1.0f / (float)max(k1 - k0, 1);
+            acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+          }
+          *reinterpret_cast<float4*>(p.aggr + ((long long)b * p.n_rec + r0 + j) * 64 + cg * 4) = acc;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      named_bar_sync(1, EPI_THREADS);
+      if (tid == 0) mbar_arrive(bar_epi_done + 8 * st);
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 12) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  });
+  return fn;
+}
+
+// rows x cols fp32 tensor with an optional batch dim; box = 32 cols x box_rows rows, 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch_elems,
+                    uint64_t bstride_elems, uint32_t box_rows, bool three_d) {
+  EncodeTiledFn enc = get_encode();
+  NLAM_REQUIRE(enc, NLAM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {row_pitch_elems * 4, bstride_elems * 4};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, three_d ? 3 : 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NLAM_REQUIRE(r == CUDA_SUCCESS, NLAM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p cols=%llu rows=%llu", (int)r, ptr,
+               (unsigned long long)cols, (unsigned long long)rows);
+  return NLAM_OK;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static bool mlp_shape_ok(const NlamMlp* m, int* nout) {
+  if (m->n_linear != 2 || m->out_dim[0] != 64) return false;
+  const int no = m->out_dim[1];
+  if (no < 1 || no > 64) return false;
+  if (m->ln_gamma && no != 64) return false;
+  if (m->in_dim % 4 != 0 || m->in_dim > 192) return false;
+  if (!aligned16(m->w[0]) || !aligned16(m->w[1]) || !aligned16(m->b[0]) || !aligned16(m->b[1])) return false;
+  if (m->ln_gamma && (!aligned16(m->ln_gamma) || !aligned16(m->ln_beta))) return false;
+  *nout = no;
+  return true;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2,
+                  const TcParams& p, cudaStream_t st) {
+  static unsigned attr_mask = 0;  // per device
+  int dev = 0;
+  NLAM_CUDA_OK(cudaGetDevice(&dev));
+  if (!(attr_mask & (1u << (dev & 31)))) {
+    NLAM_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_mask |= 1u << (dev & 31);
+  }
+  long long n_work = (long long)p.n_tiles * p.B;
+  int grid = (int)std::min<long long>(n_work, num_sms());
+  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, p);
+  count_launch();
+  NLAM_CUDA_OK(cudaGetLastError());
+  return NLAM_OK;
+}
+
+static int weight_maps(const NlamMlp* m, int nb1, int n2, int nout, CUtensorMap* w1, CUtensorMap* w2) {
+  (void)nb1;
+  int rc = make_map(w1, m->w[0], (uint64_t)m->in_dim, 64, 1, (uint64_t)m->in_dim, 0, 64, false);
+  if (rc) return rc;
+  return make_map(w2, m->w[1], 64, (uint64_t)nout, 1, 64, 0, (uint32_t)n2, false);
+}
+
+bool tc_rowmlp_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                         const NlamRowSrc* res2, int64_t n_rows) {
+  int nout = 0;
+  if (res2 || n_rows < 1 || n_rows >= (1LL << 31) - 256) return false;
+  if (!mlp_shape_ok(mlp, &nout)) return false;
+  bool all_wide = n_src <= 2;
+  for (int s = 0; s < n_src; ++s)
+    all_wide = all_wide && srcs[s].dim == 64 && !srcs[s].idx && aligned16(srcs[s].ptr) && (srcs[s].bstride % 4 == 0);
+  if (all_wide) {
+    if (res) {
+      if (nout != 64 || res->idx) return false;
+      bool match = false;
+      for (int s = 0; s < n_src; ++s) match = match || (srcs[s].ptr == res->ptr && srcs[s].bstride == res->bstride);
+      if (!match) return false;
+    }
+    return true;
+  }
+  // generic narrow concatenation (grid embedder): total width <= 64, no gathers, no residual
+  if (res || mlp->in_dim > 64) return false;
+  for (int s = 0; s < n_src; ++s)
+    if (srcs[s].idx) return false;
+  return true;
+}
+
+int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
+              int B, cudaStream_t st) {
+  int nout = 0;
+  NLAM_REQUIRE(mlp_shape_ok(mlp, &nout), NLAM_E_UNSUPPORTED, "tc_rowmlp: unsupported MLP shape");
+  NLAM_REQUIRE(aligned16(out), NLAM_E_INVALID, "tc_rowmlp: output not 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap a0, a1, w1, w2;
+  memset(&a0, 0, sizeof(a0));
+  memset(&a1, 0, sizeof(a1));
+  bool all_wide = n_src <= 2;
+  for (int s = 0; s < n_src; ++s)
+    all_wide = all_wide && srcs[s].dim == 64 && !srcs[s].idx && aligned16(srcs[s].ptr) && (srcs[s].bstride % 4 == 0);
+  p.res_block = -1;
+  if (all_wide) {
+    p.nb1 = 2 * n_src;
+    for (int s = 0; s < n_src; ++s) {
+      const bool batched = srcs[s].bstride != 0 && B > 1;
+      int rc = make_map(s == 0 ? &a0 : &a1, srcs[s].ptr, 64, (uint64_t)n_rows, batched ? (uint64_t)B : 1, 64,
+                        batched ? (uint64_t)srcs[s].bstride : (uint64_t)n_rows * 64, BM, true);
+      if (rc) return rc;
+      if (s == 0) { p.a0_blocks = 2; p.a0_batched = batched; } else { p.a1_blocks = 2; p.a1_batched = batched; }
+      if (res && res->ptr == srcs[s].ptr && res->bstride == srcs[s].bstride && p.res_block < 0) p.res_block = 2 * s;
+    }
+    NLAM_REQUIRE(!res || p.res_block >= 0, NLAM_E_UNSUPPORTED, "tc_rowmlp: residual must be one of the inputs");
+  } else {
+    p.nb1 = (mlp->in_dim + 31) / 32;
+    p.n_elem = n_src;
+    for (int s = 0; s < n_src; ++s) {
+      p.esrc[s] = srcs[s].ptr;
+      p.ebs[s] = srcs[s].bstride;
+      p.edim[s] = srcs[s].dim;
+    }
+    p.k_real = mlp->in_dim;
+  }
+  NLAM_REQUIRE(p.nb1 * 32 >= mlp->in_dim, NLAM_E_INVALID, "tc_rowmlp: width mismatch");
+  p.n2 = nout <= 32 ? 32 : 64;
+  p.nout = nout;
+  int rc = weight_maps(mlp, p.nb1, p.n2, nout, &w1, &w2);
+  if (rc) return rc;
+  p.b1 = mlp->b[0];
+  p.b2 = mlp->b[1];
+  p.gamma = mlp->ln_gamma;
+  p.beta = mlp->ln_beta;
+  p.eps = mlp->ln_eps;
+  p.out = out;
+  p.n_rows = n_rows;
+  p.B = B;
+  p.n_tiles = (int)((n_rows + BM - 1) / BM);
+  return launch(a0, a1, w1, w2, p, st);
+}
+
+bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags) {
+  int nout = 0;
+  if (flags & NLAM_PROPAGATION) return false;
+  if (!g || g->n_tiles <= 0) return false;
+  if (!mlp_shape_ok(edge_mlp, &nout) || nout != 64 || edge_mlp->in_dim != 192 || !edge_mlp->ln_gamma) return false;
+  return true;
+}
+
+int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+            int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
+            cudaStream_t st) {
+  NLAM_REQUIRE(tc_edge_supported(g, edge_mlp, flags), NLAM_E_UNSUPPORTED, "tc_edge: unsupported shape");
+  NLAM_REQUIRE(aligned16(send) && aligned16(rec) && aligned16(edge) && aligned16(aggr_out) &&
+                   (!edge_out || aligned16(edge_out)) && send_bs % 4 == 0 && rec_bs % 4 == 0 && edge_bs % 4 == 0,
+               NLAM_E_INVALID, "tc_edge: pointers / strides must be 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap a0, a1, w1, w2;
+  memset(&a1, 0, sizeof(a1));
+  const bool batched = edge_bs != 0 && B > 1;
+  int rc = make_map(&a0, edge, 64, (uint64_t)g->n_edges, batched ? (uint64_t)B : 1, 64,
+                    batched ? (uint64_t)edge_bs : (uint64_t)g->n_edges * 64, BM, true);
+  if (rc) return rc;
+  rc = weight_maps(edge_mlp, 6, 64, 64, &w1, &w2);
+  if (rc) return rc;
+  p.mode_edge = 1;
+  p.nb1 = 6;
+  p.a0_blocks = 2;
+  p.a0_batched = batched;
+  p.gsrc[0] = send; p.gbs[0] = send_bs; p.gidx[0] = g->src;
+  p.gsrc[1] = rec;  p.gbs[1] = rec_bs;  p.gidx[1] = g->dst;
+  p.b1 = edge_mlp->b[0];
+  p.b2 = edge_mlp->b[1];
+  p.gamma = edge_mlp->ln_gamma;
+  p.beta = edge_mlp->ln_beta;
+  p.eps = edge_mlp->ln_eps;
+  p.n2 = 64;
+  p.nout = 64;
+  p.res_block = 0;  // the e tile (needed for e' = e + m; harmless when edge_out is NULL)
+  p.out = edge_out;
+  p.aggr = aggr_out;
+  p.mean = (flags & NLAM_AGGR_MEAN) ? 1 : 0;
+  p.n_rows = g->n_edges;
+  p.B = B;
+  p.n_tiles = g->n_tiles;
+  p.tile_rec = g->tile_rec;
+  p.tile_e0 = g->tile_e0;
+  p.rowptr = g->rowptr;
+  p.n_rec = g->n_rec;
+  return launch(a0, a1, w1, w2, p, st);
+}
+
+}  // namespace nlam
