@@ -60,6 +60,7 @@ struct NlamGraph {
   int32_t n_tiles = 0;
   int32_t* tile_rec = nullptr;  // n_tiles+1
   int32_t* tile_e0 = nullptr;   // n_tiles+1: first CSR edge of each tile
+  int32_t* tile_meta = nullptr; // 4*n_tiles: {first edge, #edges, first receiver, #receivers}
   std::vector<int32_t> h_tile_rec, h_rowptr;
 };
 

@@ -108,6 +108,13 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
   }
   std::vector<int32_t> tile_e0(tile_rec.size());
   for (size_t i = 0; i < tile_rec.size(); ++i) tile_e0[i] = rowptr[tile_rec[i]];
+  std::vector<int32_t> tile_meta;
+  for (size_t i = 0; i + 1 < tile_rec.size(); ++i) {
+    tile_meta.push_back(tile_e0[i]);
+    tile_meta.push_back(tile_e0[i + 1] - tile_e0[i]);
+    tile_meta.push_back(tile_rec[i]);
+    tile_meta.push_back(tile_rec[i + 1] - tile_rec[i]);
+  }
   g->h_tile_rec = tile_rec;
   g->h_rowptr = rowptr;
 
@@ -128,7 +135,8 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
   if ((rc = upload(&g->rowptr, rowptr)) || (rc = upload(&g->src, src)) || (rc = upload(&g->dst, dst)) ||
       (rc = upload(&g->perm, perm)) || (rc = upload(&g->inv_perm, inv_perm)) ||
       (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
-      (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0))) {
+      (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0)) ||
+      (rc = upload(&g->tile_meta, tile_meta))) {
     cudaSetDevice(prev_dev);
     nlam_graph_destroy(g);
     return rc;
@@ -152,6 +160,7 @@ extern "C" void nlam_graph_destroy(NlamGraph* g) {
   cudaFree(g->sperm);
   cudaFree(g->tile_rec);
   cudaFree(g->tile_e0);
+  cudaFree(g->tile_meta);
   cudaSetDevice(prev);
   delete g;
 }

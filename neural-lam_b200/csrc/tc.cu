@@ -13,13 +13,13 @@
 //     a = up to two 64-wide row blocks by TMA (e.g. [rec | aggr]) or a generic concatenation
 //     of narrow inputs (grid features 17|17|18|4); optional residual, optional LayerNorm.
 //
-// Warp roles (448 threads, 1 CTA / SM, persistent over (batch, tile) work items):
-//   warps 0-7   epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/SiLU/LayerNorm/residual,
+// Warp roles (704 threads, 1 CTA / SM, persistent over (batch, tile) work items):
+//   warps 0-15  epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/SiLU/LayerNorm/residual,
 //               segmented reduction, coalesced stores.  warp%4 selects the TMEM lane quarter,
-//               warp/4 the column half.
-//   warps 8-11  producers: index-driven gathers (cp.async 16 B, manual 128B swizzle)
-//   warp 12     TMEM allocation + single-thread tcgen05.mma issue
-//   warp 13     TMA loads (weights once, A tiles per work item)
+//               warp/4 the 16-column quarter.
+//   warps 16-19 producers: index-driven gathers (cp.async 16 B, manual 128B swizzle)
+//   warp 20     TMEM allocation + single-thread tcgen05.mma issue
+//   warp 21     TMA loads (weights once, A tiles per work item)
 //
 // Shared memory (dynamic, 1024-byte aligned): W1 6x8 KB | W2 2x8 KB | A 8x16 KB | HB 2x16 KB |
 // barriers + LayerNorm exchange + local CSR offsets = 227 KB.  TMA-loaded A blocks are double
@@ -28,6 +28,7 @@
 // TMEM accumulators (D1/D2 of stage s at columns s*128 / s*128+64), so that the TMA loads, the
 // gathers and the first GEMM of tile i+1 overlap the epilogue of tile i.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -35,8 +36,9 @@
 
 namespace nlam {
 
-constexpr int TC_THREADS = 448;
-constexpr int EPI_THREADS = 256;
+constexpr int TC_THREADS = 704;
+constexpr int EPI_THREADS = 512;
+constexpr int EPI_WARPS = EPI_THREADS / 32;
 constexpr int PROD_THREADS = 128;
 constexpr int BM = 128;
 constexpr uint32_t A_BLOCK = 16384;  // 128 rows x 128 B
@@ -81,8 +83,10 @@ struct TcParams {
   int n_tiles;
   const int32_t* tile_rec;
   const int32_t* tile_e0;  // first CSR edge of each tile (n_tiles+1)
+  const int4* tile_meta;   // {first edge, #edges, first receiver, #receivers} per tile
   const int32_t* rowptr;
   long long n_rec;
+  long long* dbg;  // optional per-phase clock64 timeline of block 0 (bring-up / profiling aid)
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -119,7 +123,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
       : "r"(bar), "r"(parity)
@@ -145,6 +149,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -196,15 +208,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // byte offset of 16-byte chunk `ch` (0..7) of row `row` inside a 128B-swizzled [128][32 float] block
 __device__ __forceinline__ uint32_t swz(int row, int ch) { return (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4)); }
 
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) {
+  // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx.f32, rel. error ~2^-11 — the
+  // size of the TF32 rounding the value undergoes anyway as the second GEMM's operand)
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+#define NLAM_DBG(slot, it)                                                      \
+  do {                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+              const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x;
@@ -222,7 +259,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const uint32_t bar_d1_full = mb + 64;
   const uint32_t bar_d2_full = mb + 80;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 96);
-  float* ln_x = reinterpret_cast<float*>(smem + OFF_MISC + 128);   // [2 stats][2 halves][128 rows]
+  float* ln_x = reinterpret_cast<float*>(smem + OFF_MISC + 128);   // [4 column quarters][128 rows]
   int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 128 + 2048);  // local CSR offsets, <= 129 entries
 
   if ((sbase & 1023u) != 0) {
@@ -233,7 +270,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const bool has_tma_a = (p.a0_blocks + p.a1_blocks) > 0;
   const bool has_prod = p.mode_edge || p.n_elem > 0;
 
-  if (warp == 12) {
+  if (warp == EPI_WARPS + 4) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
       mbar_init(bar_a_gat_full, PROD_THREADS);
@@ -253,11 +290,12 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 13 && lane == 0) {
+  if (warp == EPI_WARPS + 5 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     if (p.a0_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     if (p.a1_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    if (p.out && p.nout == 64) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -266,9 +304,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   // first A block of TMA stage st (edge mode keeps the gathered blocks 2-5 single buffered)
   const int stage_blk1 = p.mode_edge ? 6 : p.nb1;
 
-  const long long n_work = (long long)p.n_tiles * p.B;
+  const int n_work = p.n_tiles * p.B;  // host guarantees < 2^31
 
-  if (warp == 13) {
+  if (warp == EPI_WARPS + 5) {
     // =============================== TMA loader ===============================
     if (lane == 0) {
       const uint32_t w2_block_bytes = (uint32_t)p.n2 * 128u;
@@ -277,14 +315,15 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * W_BLOCK, &tmW2, bar_w, 32 * j, 0);
       if (has_tma_a) {
         int it = 0;
-        for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-          const int b = (int)(w / p.n_tiles);
-          const int t = (int)(w - (long long)b * p.n_tiles);
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+          const int b = w / p.n_tiles;
+          const int t = w - b * p.n_tiles;
           const int st = it & 1;
           const int row0 = p.mode_edge ? p.tile_e0[t] : t * BM;
           const uint32_t abase = sbase + OFF_A + (st ? stage_blk1 : 0) * A_BLOCK;
           const uint32_t full = bar_a_tma_full + 8 * st;
           mbar_wait(bar_epi_done + 8 * st, (uint32_t)(((it >> 1) & 1) ^ 1));  // tile it-2 released the stage
+          NLAM_DBG(0, it);
           mbar_expect_tx(full, (uint32_t)(p.a0_blocks + p.a1_blocks) * A_BLOCK);
           for (int j = 0; j < p.a0_blocks; ++j)
             tma_load_3d(abase + j * A_BLOCK, &tmA0, full, 32 * j, row0, p.a0_batched ? b : 0);
@@ -293,7 +332,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == EPI_WARPS + 4) {
     // =============================== MMA issuer ===============================
     // Software pipelined: GEMM1 of tile i+1 is issued as soon as its operands have landed,
     // GEMM2 of tile i as soon as the epilogue has produced the hidden activations.
@@ -301,7 +340,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const uint32_t idesc1 = umma_idesc_tf32(BM, 64);
       const uint32_t idesc2 = umma_idesc_tf32(BM, p.n2);
       int n_my = 0;
-      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
       mbar_wait(bar_w, 0);
       int g1 = 0, g2 = 0;
       uint32_t idle = 0;
@@ -316,6 +355,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (ready && has_prod) ready = mbar_test(bar_a_gat_full, (uint32_t)(it & 1));
           if (ready) {
             tc_fence_after();
+            NLAM_DBG(3, it);
             const uint32_t d1 = tmem_base + st * 128;
             for (int j = 0; j < p.nb1; ++j) {
               // A block j: TMA blocks come from the stage, produced blocks (edge gathers) are fixed
@@ -339,6 +379,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           const int it = g2, st = it & 1;
           if (mbar_test(bar_hb_full, (uint32_t)(it & 1))) {
             tc_fence_after();
+            NLAM_DBG(4, it);
             const uint32_t d2 = tmem_base + st * 128 + 64;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -361,18 +402,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= EPI_WARPS) {
     // =============================== producers ===============================
     if (has_prod) {
-      const int pt = tid - 8 * 32;  // 0..127
+      const int pt = tid - EPI_THREADS;  // 0..127
       int it = 0;
-      for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int b = (int)(w / p.n_tiles);
-        const int t = (int)(w - (long long)b * p.n_tiles);
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int b = w / p.n_tiles;
+        const int t = w - b * p.n_tiles;
         mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
+        if (pt == 0) NLAM_DBG(1, it);
         if (p.mode_edge) {
           const int e0 = p.tile_e0[t];
-          const int ne = p.tile_e0[t + 1] - e0;
+          const int ne = (int)min((long long)BM, p.n_rows - e0);  // whole window, clipped at the end
           // each warp owns 32 tile rows; a half-warp copies one 256-byte row per instruction
           const int pw = pt >> 5;
           const int my_row = pw * 32 + lane;
@@ -417,97 +459,123 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           }
         }
         fence_proxy_async();
+        if (pt == 0) NLAM_DBG(2, it);
         mbar_arrive(bar_a_gat_full);
       }
     }
   } else {
-    // =============================== epilogue (warps 0-7) ===============================
-    const int q = warp & 3;        // TMEM lane quarter
-    const int half = warp >> 2;    // column half
-    const int row = q * 32 + lane;  // tile row owned by this thread
-    const int c0 = half * 32;
+    // =============================== epilogue (warps 0-15) ===============================
+    // thread = (tile row, 16-column quarter): warp%4 selects the TMEM lane quarter (hardware
+    // restriction of tcgen05.ld), warp/4 the column quarter.
+    const int q = warp & 3;
+    const int cq = warp >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = cq * 16;
+    const int blk = cq >> 1;             // 32-column block holding this thread's columns
+    const int ch0 = (cq & 1) * 4;        // first 16-byte chunk inside that block
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    const uint32_t rsw = (uint32_t)(row * 128);
+    const int rx = row & 7;
+    const int lnbar = 2 + q;  // LayerNorm exchange only couples the 4 warps of one lane quarter
+
+    // per-tile metadata {first row, #rows, first receiver, #receivers}, prefetched one tile ahead
+    auto load_meta = [&](int w) -> int4 {
+      const int t = w % p.n_tiles;
+      if (p.mode_edge) return __ldg(p.tile_meta + t);
+      const long long r0 = (long long)t * BM;
+      return make_int4((int)r0, (int)min((long long)BM, p.n_rows - r0), 0, 0);
+    };
+    int4 meta = make_int4(0, 0, 0, 0);
+    int lp_val = 0;
+    if ((int)blockIdx.x < n_work) {
+      meta = load_meta(blockIdx.x);
+      if (p.mode_edge && tid <= meta.w) lp_val = __ldg(p.rowptr + meta.z + tid) - meta.x;
+    }
     int it = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const uint32_t ph = (uint32_t)(it & 1);
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
       const uint32_t tmem_d1 = tmem_base + st * 128;
       const uint32_t tmem_d2 = tmem_d1 + 64;
-      const int b = (int)(w / p.n_tiles);
-      const int t = (int)(w - (long long)b * p.n_tiles);
-      long long row0;
-      int nrows, r0 = 0, nrec = 0;
-      if (p.mode_edge) {
-        r0 = p.tile_rec[t];
-        nrec = p.tile_rec[t + 1] - r0;
-        const int e0 = p.tile_e0[t];
-        row0 = e0;
-        nrows = p.tile_e0[t + 1] - e0;
-        if (tid <= nrec) lp[tid] = p.rowptr[r0 + tid] - e0;
-      } else {
-        row0 = (long long)t * BM;
-        nrows = (int)min((long long)BM, p.n_rows - row0);
-      }
+      const int b = w / p.n_tiles;
+      const int row0 = meta.x, nrows = meta.y, r0 = meta.z, nrec = meta.w;
+      const int cur_lp = lp_val;
+      // prefetch the next tile's metadata (consumed at the end of this iteration)
+      const int wn = w + (int)gridDim.x;
+      int4 meta_n = meta;
+      if (wn < n_work) meta_n = load_meta(wn);
 
       // ---- E1: hidden = SiLU(D1 + b1) -> HB (UMMA A operand layout) ----
+      if (tid == 0) NLAM_DBG(5, it);
       mbar_wait(bar_d1_full + 8 * st, sph);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_d1 + t_lane + c0, v);
+      if (tid == 0) NLAM_DBG(6, it);
+      float v[16];
+      tmem_ld16(tmem_d1 + t_lane + c0, v);
       {
-        uint8_t* hb = smem + OFF_HB + half * A_BLOCK;
+        uint8_t* hb = smem + OFF_HB + blk * A_BLOCK + rsw;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           float4 o;
           const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c0 + 4 * k));
           o.x = silu_fast(v[4 * k + 0] + bb.x);
           o.y = silu_fast(v[4 * k + 1] + bb.y);
           o.z = silu_fast(v[4 * k + 2] + bb.z);
           o.w = silu_fast(v[4 * k + 3] + bb.w);
-          *reinterpret_cast<float4*>(hb + swz(row, k)) = o;
+          *reinterpret_cast<float4*>(hb + (((ch0 + k) ^ rx) << 4)) = o;
         }
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_hb_full);
+      if (tid == 0) NLAM_DBG(7, it);
+      if (p.mode_edge) {
+        if (tid <= nrec) lp[tid] = cur_lp;  // the previous tile's reduction has passed its final barrier
+        if (wn < n_work && tid <= meta_n.w) lp_val = __ldg(p.rowptr + meta_n.z + tid) - meta_n.x;
+      }
 
       // ---- E2: y = D2 + b2, LayerNorm, residual ----
       mbar_wait(bar_d2_full + 8 * st, sph);
       tc_fence_after();
+      if (tid == 0) NLAM_DBG(8, it);
       const bool active = c0 < p.n2;
-      if (active) tmem_ld32(tmem_d2 + t_lane + c0, v);
-      if (active) {
+      const bool wide = (p.nout == 64);
+      if (active) tmem_ld16(tmem_d2 + t_lane + c0, v);
+      if (wide) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (c0 + 4 * k < p.nout) {  // nout is a multiple of 4 when it is 64; ragged (17) handled per element
-            const float* b2p = p.b2 + c0 + 4 * k;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (c0 + 4 * k + i < p.nout) v[4 * k + i] += __ldg(b2p + i);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 4 * k));
+          v[4 * k + 0] += bb.x;
+          v[4 * k + 1] += bb.y;
+          v[4 * k + 2] += bb.z;
+          v[4 * k + 3] += bb.w;
         }
+      } else if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.nout) v[i] += __ldg(p.b2 + c0 + i);
       }
       if (p.gamma) {
-        // two-pass LayerNorm over 64 columns split across the two column halves
+        // two-pass LayerNorm over 64 columns split across the four column quarters
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s += v[i];
-        ln_x[half * BM + row] = s;
-        named_bar_sync(1, EPI_THREADS);
-        const float mu = (ln_x[row] + ln_x[BM + row]) * (1.0f / 64.0f);
+        for (int i = 0; i < 16; ++i) s += v[i];
+        ln_x[cq * BM + row] = s;
+        named_bar_sync(lnbar, 128);
+        const float mu = (ln_x[row] + ln_x[BM + row] + ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
         float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           v[i] -= mu;
           sq += v[i] * v[i];
         }
-        ln_x[2 * BM + half * BM + row] = sq;
-        named_bar_sync(1, EPI_THREADS);
-        const float var = (ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
+        named_bar_sync(lnbar, 128);  // the quarter has read the sums; the array is reused
+        ln_x[cq * BM + row] = sq;
+        named_bar_sync(lnbar, 128);
+        const float var = (ln_x[row] + ln_x[BM + row] + ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
         const float rstd = rsqrtf(var + p.eps);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4 * k));
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * k));
           v[4 * k + 0] = v[4 * k + 0] * rstd * g4.x + b4.x;
@@ -516,25 +584,27 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           v[4 * k + 3] = v[4 * k + 3] * rstd * g4.w + b4.w;
         }
       }
+      if (tid == 0) NLAM_DBG(9, it);
 
       // staging: messages (edge mode) -> HB; output rows -> residual blocks in place, or HB
-      const bool wide = (p.nout == 64);
-      uint8_t* stage = nullptr;  // where the 64-wide output tile is staged (swizzled block pair)
+      uint32_t stage = 0;  // shared address of the staged 64-wide output tile (swizzled block pair)
       if (wide) {
         if (p.mode_edge) {
-          uint8_t* hb = smem + OFF_HB + half * A_BLOCK;
+          uint8_t* hb = smem + OFF_HB + blk * A_BLOCK + rsw;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(hb + swz(row, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(hb + (((ch0 + k) ^ rx) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
         if (p.res_block >= 0) {
-          if (has_tma_a) mbar_wait(bar_a_tma_full + 8 * st, sph);  // TMA-written rows visible to this thread
-          stage = smem + OFF_A + ((st ? stage_blk1 : 0) + p.res_block) * A_BLOCK;
+          const uint32_t soff = OFF_A + ((st ? stage_blk1 : 0) + p.res_block) * A_BLOCK;
+          stage = sbase + soff;
           if (p.out) {
-            uint8_t* rb = stage + half * A_BLOCK;
+            if (has_tma_a) mbar_wait(bar_a_tma_full + 8 * st, sph);  // TMA-written rows visible to this thread
+            uint8_t* rb = smem + soff + blk * A_BLOCK + rsw;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              float4* ptr = reinterpret_cast<float4*>(rb + swz(row, k));
+            for (int k = 0; k < 4; ++k) {
+              float4* ptr = reinterpret_cast<float4*>(rb + (((ch0 + k) ^ rx) << 4));
               float4 r = *ptr;
               r.x += v[4 * k];
               r.y += v[4 * k + 1];
@@ -544,44 +614,49 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             }
           }
         } else if (!p.mode_edge) {
-          stage = smem + OFF_HB;
-          uint8_t* hb = stage + half * A_BLOCK;
+          stage = sbase + OFF_HB;
+          uint8_t* hb = smem + OFF_HB + blk * A_BLOCK + rsw;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(hb + swz(row, k)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(hb + (((ch0 + k) ^ rx) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
       } else if (active) {
         // narrow output (e.g. output_map 64 -> 17): plain [128][nout] floats in HB, odd pitch
         float* flat = reinterpret_cast<float*>(smem + OFF_HB);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < 16; ++i)
           if (c0 + i < p.nout) flat[row * p.nout + c0 + i] = v[i];
       }
+      fence_proxy_async();  // staged tile -> async proxy (TMA store)
       named_bar_sync(1, EPI_THREADS);
+      if (tid == 0) NLAM_DBG(10, it);
 
-      // ---- coalesced copy-out ----
+      // ---- output: one TMA tensor store per 32-column block (full 128-row box, clipped at the
+      // tensor end; in edge mode the rows past the tile's own edges belong to the following
+      // tiles and carry the identical values those tiles store) ----
       if (p.out) {
-        if (wide && stage) {
-          float* og = p.out + ((long long)b * p.n_rows + row0) * 64;
-          for (int i = tid; i < nrows * 16; i += EPI_THREADS) {
-            const int r = i >> 4, ch = i & 15;
-            const float4 val = *reinterpret_cast<const float4*>(stage + (ch >> 3) * A_BLOCK + swz(r, ch & 7));
-            *reinterpret_cast<float4*>(og + (long long)r * 64 + ch * 4) = val;
+        if (wide) {
+          if (tid == 0 && stage) {
+            tma_store_3d(&tmOut, stage, 0, row0, b);
+            tma_store_3d(&tmOut, stage + A_BLOCK, 32, row0, b);
+            bulk_commit();
           }
-        } else if (!wide) {
+        } else {
           const float* flat = reinterpret_cast<const float*>(smem + OFF_HB);
           float* og = p.out + ((long long)b * p.n_rows + row0) * p.nout;
           const int n = nrows * p.nout;
           for (int i = tid; i < n; i += EPI_THREADS) og[i] = flat[i];
         }
       }
+      if (tid == 0) NLAM_DBG(11, it);
       // ---- segmented sum of the messages over the tile's receivers (CSR order) ----
       if (p.mode_edge) {
-        // thread = (float4 column group cg, receiver group g): 16 x 16
+        // thread = (float4 column group cg, receiver group g): 16 x 32
         const int cg = tid & 15, g = tid >> 4;
         const uint8_t* mbase = smem + OFF_HB + (cg >> 3) * A_BLOCK;
         const int chq = cg & 7;
-        for (int j = g; j < nrec; j += 16) {
+        for (int j = g; j < nrec; j += EPI_THREADS / 16) {
           const int k0 = lp[j], k1 = lp[j + 1];
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int k = k0; k < k1; ++k) {
@@ -595,18 +670,26 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           *reinterpret_cast<float4*>(p.aggr + ((long long)b * p.n_rec + r0 + j) * 64 + cg * 4) = acc;
         }
       }
-      fence_proxy_async();
+      if (tid == 0) {
+        NLAM_DBG(12, it);
+        if (p.out && wide && stage) bulk_wait_read0();  // staged tile fully read by the TMA engine
+      }
       tc_fence_before();
       named_bar_sync(1, EPI_THREADS);
-      if (tid == 0) mbar_arrive(bar_epi_done + 8 * st);
+      if (tid == 0) {
+        NLAM_DBG(13, it);
+        mbar_arrive(bar_epi_done + 8 * st);
+      }
+      meta = meta_n;
     }
+    if (tid == 0) bulk_wait0();  // all output stores complete before the CTA retires
   }
 
   // teardown
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 12) {
+  if (warp == EPI_WARPS + 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
@@ -672,7 +755,7 @@ static int num_sms() {
 }
 
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2,
-                  const TcParams& p, cudaStream_t st) {
+                  const CUtensorMap& om, const TcParams& p, cudaStream_t st) {
   static unsigned attr_mask = 0;  // per device
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
@@ -681,8 +764,31 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     attr_mask |= 1u << (dev & 31);
   }
   long long n_work = (long long)p.n_tiles * p.B;
+  NLAM_REQUIRE(n_work < (1LL << 31) - 4096, NLAM_E_UNSUPPORTED, "tc kernel: too many work items (%lld)", n_work);
   int grid = (int)std::min<long long>(n_work, num_sms());
-  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, p);
+  TcParams pp = p;
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("NLAM_TC_TIMELINE") ? 1 : 0;
+  if (dbg_on) {
+    if (!dbg_buf) NLAM_CUDA_OK(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+    NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
+    pp.dbg = dbg_buf;
+  }
+  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, om, pp);
+  if (dbg_on) {
+    long long h[256];
+    NLAM_CUDA_OK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NLAM_CUDA_OK(cudaStreamSynchronize(st));
+    long long t0 = h[0] ? h[0] : h[1];
+    fprintf(stderr, "[nlam tc timeline] mode_edge=%d nb1=%d grid=%d work=%lld (cycles rel. to first event)\n", p.mode_edge, p.nb1, grid, n_work);
+    fprintf(stderr, " it    tma  g_start g_done   g1_iss  g2_iss | e_wait  d1_rdy  e1_done d2_rdy  ln_done staged  copied  reduced end\n");
+    for (int it = 0; it < 8; ++it) {
+      fprintf(stderr, "%3d ", it);
+      for (int k = 0; k < 14; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
@@ -768,7 +874,13 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
   p.n_rows = n_rows;
   p.B = B;
   p.n_tiles = (int)((n_rows + BM - 1) / BM);
-  return launch(a0, a1, w1, w2, p, st);
+  CUtensorMap om;
+  memset(&om, 0, sizeof(om));
+  if (nout == 64) {
+    rc = make_map(&om, out, 64, (uint64_t)n_rows, (uint64_t)B, 64, (uint64_t)n_rows * 64, BM, true);
+    if (rc) return rc;
+  }
+  return launch(a0, a1, w1, w2, om, p, st);
 }
 
 bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags) {
@@ -818,9 +930,16 @@ int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int6
   p.n_tiles = g->n_tiles;
   p.tile_rec = g->tile_rec;
   p.tile_e0 = g->tile_e0;
+  p.tile_meta = reinterpret_cast<const int4*>(g->tile_meta);
   p.rowptr = g->rowptr;
   p.n_rec = g->n_rec;
-  return launch(a0, a1, w1, w2, p, st);
+  CUtensorMap om;
+  memset(&om, 0, sizeof(om));
+  if (edge_out) {
+    rc = make_map(&om, edge_out, 64, (uint64_t)g->n_edges, (uint64_t)B, 64, (uint64_t)g->n_edges * 64, BM, true);
+    if (rc) return rc;
+  }
+  return launch(a0, a1, w1, w2, om, p, st);
 }
 
 }  // namespace nlam

@@ -1,0 +1,187 @@
+"""Parity of the tcgen05 (TF32 tensor-core) kernels, through the C ABI, against the CPU oracle.
+
+Stated tolerance (TF32 inputs, fp32 accumulate; LayerNorm outputs are O(1)):
+  * |kernel - fp64 oracle| <= 1e-2 absolute per InteractionNet call, and
+  * <= 3x the error the REFERENCE's own GPU configuration makes on the same inputs: the oracle
+    op sequence run by torch on the GPU with TF32 matmuls enabled, as the reference enables them
+    whenever CUDA is available (reference neural_lam/train_model.py:484-488).
+"""
+import pytest
+import torch
+
+import neural_lam_b200 as nlb
+from neural_lam_b200 import _lib, models, ops, synthetic
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ABS_TOL = 1e-2
+
+
+def _ref_tf32_err(fn64, fn_gpu):
+    """error of the reference-style torch TF32 GPU evaluation vs the fp64 oracle"""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        got = fn_gpu()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    want = fn64()
+    if isinstance(got, torch.Tensor):
+        got, want = (got,), (want,)
+    return max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want)), want
+
+
+def _graph(ns, nr, ne, seed, sort):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.stack([torch.randint(0, ns, (ne,), generator=g), torch.randint(0, nr, (ne,), generator=g)])
+    ei[1, -1] = nr - 1
+    if sort:
+        ei = ei[:, torch.sort(ei[1], stable=True).indices]
+    return ei
+
+
+CASES = [
+    # name, ns, nr, ne, B, update_edges, aggr, same nodes, sorted, expanded edge
+    ("sum_upd", 50, 30, 400, 2, True, "sum", False, True, False),
+    ("mean_noupd", 50, 30, 400, 2, False, "mean", False, True, False),
+    ("m2m_same", 200, 200, 1800, 3, True, "sum", True, True, False),
+    ("unsorted", 60, 40, 500, 2, True, "sum", False, False, False),
+    ("expanded_edge", 60, 40, 500, 3, True, "sum", False, True, True),
+    ("empty_receivers", 40, 600, 300, 2, True, "sum", False, True, False),
+    ("single_tile", 5, 4, 10, 1, True, "sum", False, True, False),
+    ("deg128", 300, 3, 300, 2, False, "sum", False, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_edge_and_node_kernels_vs_oracle(case):
+    name, ns, nr, ne, B, upd, aggr, same, srt, expand = case
+    ei = _graph(ns, nr, ne, 1, srt)
+    torch.manual_seed(0)
+    net = nlb.InteractionNet(ei, 64, update_edges=upd, aggr=aggr, math="tf32")
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    send = torch.randn(B, ns, 64)
+    rec = send if same else torch.randn(B, nr, 64)
+    edge = torch.randn(1 if expand else B, ne, 64)
+    sd = dict(net.state_dict())
+    sd64 = {k: v.double() for k, v in sd.items()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+
+    def f64():
+        return rp.interaction_net(sd64, ei, send.double(), rec.double(), edge.double().expand(B, -1, -1), aggr=aggr,
+                                  update_edges=upd)
+
+    def fgpu():
+        return rp.interaction_net(sdg, ei.to(DEV), send.to(DEV), rec.to(DEV), edge.to(DEV).expand(B, -1, -1),
+                                  aggr=aggr, update_edges=upd)
+
+    ref_err, want = _ref_tf32_err(f64, fgpu)
+    net = net.to(DEV)
+    with torch.no_grad():
+        got = net(send.to(DEV), (send if same else rec).to(DEV), edge.to(DEV).expand(B, -1, -1))
+    got = got if isinstance(got, tuple) else (got,)
+    err = max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want))
+    assert err <= ABS_TOL, (name, err)
+    assert err <= 3 * ref_err + 1e-4, (name, err, ref_err)
+
+
+def test_tf32_requested_but_unsupported_raises_and_auto_falls_back():
+    ei = _graph(50, 3, 500, 0, True)  # in-degree > 128: outside the tensor-core tile table
+    for H, ok_auto in ((64, True), (16, True)):
+        net_auto = nlb.InteractionNet(ei, H, math="auto").to(DEV)
+        x = [torch.randn(50, H, device=DEV), torch.randn(3, H, device=DEV), torch.randn(500, H, device=DEV)]
+        r, e = net_auto(*x)
+        r_o, e_o = rp.interaction_net({k: v.cpu() for k, v in net_auto.state_dict().items()}, ei, *[t.cpu() for t in x])
+        torch.testing.assert_close(r.cpu(), r_o, rtol=2e-5, atol=2e-5)  # exact-fp32 kernels were used
+        net_tf = nlb.InteractionNet(ei, H, math="tf32").to(DEV)
+        with pytest.raises(_lib.NlamError, match="not supported by the tcgen05"):
+            net_tf(*x)
+
+
+ROW_CASES = [
+    ("embed_ln", [64, 64, 64], [(3, 300, 64)], None, True),
+    ("embed_res", [64, 64, 64], [(2, 1000, 64)], 0, True),
+    ("node_res_rec", [128, 64, 64], [(2, 777, 64), (2, 777, 64)], 0, True),
+    ("node_res_aggr", [128, 64, 64], [(2, 130, 64), (2, 130, 64)], 1, True),
+    ("node_bcast", [128, 64, 64], [(257, 64), (3, 257, 64)], None, True),
+    ("output_map_17", [64, 64, 17], [(2, 500, 64)], None, False),
+    ("grid_embedder_56", [56, 64, 64], [(2, 400, 17), (2, 400, 17), (2, 400, 18), (400, 4)], None, True),
+    ("one_row", [64, 64, 64], [(1, 1, 64)], None, True),
+]
+
+
+@pytest.mark.parametrize("case", ROW_CASES, ids=[c[0] for c in ROW_CASES])
+def test_row_kernel_vs_oracle(case):
+    name, bp, shapes, res_idx, ln = case
+    torch.manual_seed(0)
+    m = nlb.make_mlp(bp, layer_norm=ln)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    srcs = [torch.randn(*s) for s in shapes]
+    B = max([s.shape[0] for s in srcs if s.dim() == 3], default=1)
+    cat = torch.cat([s if s.dim() == 3 else s.unsqueeze(0).expand(B, -1, -1) for s in srcs], dim=-1)
+    res = None if res_idx is None else srcs[res_idx]
+    p64 = {f"m.{k}": v.double() for k, v in m.state_dict().items()}
+    pg = {f"m.{k}": v.to(DEV) for k, v in m.state_dict().items()}
+
+    def f64():
+        y = rp.mlp(cat.double(), p64, "m", layer_norm=ln)
+        return y if res is None else y + res.double()
+
+    def fgpu():
+        y = rp.mlp(cat.to(DEV), pg, "m", layer_norm=ln)
+        return y if res is None else y + res.to(DEV)
+
+    ref_err, (want,) = _ref_tf32_err(f64, fgpu)
+    m = m.to(DEV)
+    ds = [s.to(DEV) for s in srcs]
+    with torch.no_grad():
+        got = ops.rowmlp(m, ds, res=None if res_idx is None else ds[res_idx], flags=_lib.MATH_TF32)
+    err = (got.double().cpu().reshape(want.shape) - want).abs().max().item()
+    assert err <= ABS_TOL, (name, err)
+    assert err <= 3 * ref_err + 1e-4, (name, err, ref_err)
+
+
+@pytest.mark.parametrize("kind", ["graph_lam", "hi_lam"])
+def test_model_rollout_tf32_vs_oracle(kind):
+    """Whole forecast steps (hidden 64 -> every GNN / grid MLP on the tensor-core kernels), 2 AR
+    steps, against the fp64 oracle; bound = 3x the reference-style torch TF32 GPU error."""
+    spec = synthetic.make_graph_spec(30, 27, hierarchical=(kind == "hi_lam"))
+    ds = synthetic.SyntheticDatastore(spec, d_state=17, d_forcing=18, d_static=4, boundary_width=2)
+    torch.manual_seed(42)
+    cls = models.HiLAM if kind == "hi_lam" else models.GraphLAM
+    m = cls(ds, spec, hidden_dim=64, processor_layers=2, math="auto")
+    fc = models.ARForecaster(m, ds)
+    from test_models import _oracle_graph
+
+    g = _oracle_graph(m, fc)
+    cfg = dict(model=kind, hidden_layers=1, processor_layers=2, mesh_aggr="sum")
+    G = m.num_grid_nodes
+    gen = torch.Generator().manual_seed(123)
+    B, T = 2, 2
+    init, forc, bnd = torch.randn(B, 2, G, 17, generator=gen), torch.randn(B, T, G, 18, generator=gen), torch.randn(B, T, G, 17, generator=gen)
+    params = {f"predictor.{k}": v for k, v in m.state_dict().items()}
+    gd = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in g.items()}
+
+    def f64():
+        return rp.ar_rollout({k: v.double() for k, v in params.items()}, g, cfg, init.double(), forc.double(), bnd.double())
+
+    def fgpu():
+        return rp.ar_rollout({k: v.to(DEV) for k, v in params.items()}, gd, cfg, init.to(DEV), forc.to(DEV), bnd.to(DEV))
+
+    ref_err, (want,) = _ref_tf32_err(f64, fgpu)
+    fc = fc.to(DEV)
+    n0 = _lib.lib().nlam_launch_count()
+    with torch.no_grad():
+        got, _ = fc(init.to(DEV), forc.to(DEV), bnd.to(DEV))
+        got_g = fc.rollout_graphed(init.to(DEV), forc.to(DEV), bnd.to(DEV))
+    assert _lib.lib().nlam_launch_count() > n0
+    err = (got.double().cpu() - want).abs().max().item()
+    assert err <= 5e-2 and err <= 3 * ref_err + 1e-3, (err, ref_err)
+    torch.testing.assert_close(got_g, got, rtol=1e-6, atol=1e-6)
