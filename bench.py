@@ -137,9 +137,23 @@ def time_cpu_reference(params, g, cfg, G, steps, warmup, B=1):
     index_add_) on all host cores.  Returns (steps/sec, seconds per step, cores)."""
     from oracle import reference_port as rp
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     init, forc, bnd = synth_inputs(B, max(1, steps + warmup), G)
+    # "all the host threads it can use": torch's intra-op pool does not scale to 100+ threads on
+    # these small ops, so probe a few pool sizes with one step each and keep the fastest
+    best = (None, 1e30)
+    with torch.no_grad():
+        for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+            torch.set_num_threads(nt)
+            t0 = time.perf_counter()
+            rp.ar_rollout(params, g, cfg, init, forc[:, :1], bnd[:, :1])
+            dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (nt, dt)
+            if dt > 20:  # keep the probe bounded
+                continue
+    cores = best[0]
+    torch.set_num_threads(cores)
     with torch.no_grad():
         if warmup:
             rp.ar_rollout(params, g, cfg, init, forc[:, :warmup], bnd[:, :warmup])
@@ -249,26 +263,15 @@ def run_ours(args):
         clocks = clk.summary()
 
         # ------------------------------------------------------------------ end-to-end (host buffers)
-        h_out = torch.empty(B, G, D_STATE).pin_memory()
-        stream = torch.cuda.current_stream(device)
-
-        def e2e_steps(t0, n):
-            for i in range(t0, t0 + n):
-                bufs["forcing"].copy_(forc[:, i], non_blocking=True)      # H2D from pinned memory
-                bufs["boundary"].copy_(bnd[:, i], non_blocking=True)     # H2D
-                graph.replay()
-                h_out.copy_(bufs["out"], non_blocking=True)               # D2H of the step result
-                bufs["prev_prev"].copy_(bufs["prev"])
-                bufs["prev"].copy_(bufs["out"])
-            stream.synchronize()
-
-        bufs["prev_prev"].copy_(init[:, 0], non_blocking=True)
-        bufs["prev"].copy_(init[:, 1], non_blocking=True)
-        e2e_steps(0, W)
+        # public API: ARForecaster.rollout_from_host — pinned host tensors in, pinned host tensor
+        # out; per step H2D(forcing, boundary) + graph replay + D2H(prediction) in the timed region
+        h_out = torch.empty(B, K, G, D_STATE).pin_memory()
+        h_warm = torch.empty(B, W, G, D_STATE).pin_memory()
+        fc.rollout_from_host(init, forc[:, :W], bnd[:, :W], out=h_warm)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        e2e_steps(W, K)
+        fc.rollout_from_host(init, forc[:, W:], bnd[:, W:], out=h_out)
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)

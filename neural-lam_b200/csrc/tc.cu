@@ -21,11 +21,13 @@
 //   warp 20     TMEM allocation + single-thread tcgen05.mma issue
 //   warp 21     TMA loads (weights once, A tiles per work item)
 //
+// The hidden activations never touch shared memory: the first epilogue writes SiLU(D1+b1) back to
+// TMEM (tcgen05.st) and the second GEMM reads its A operand from TMEM (tcgen05.mma "TS" form).
 // Shared memory (dynamic, 1024-byte aligned): W1 6x8 KB | W2 2x8 KB | A 8x16 KB | HB 2x16 KB |
 // barriers + LayerNorm exchange + local CSR offsets = 227 KB.  TMA-loaded A blocks are double
 // buffered (edge mode: e tile stage 0 = blocks 0-1, stage 1 = blocks 6-7, gathered sender /
 // receiver rows = blocks 2-5; row mode: stage s = blocks [s*nb1, (s+1)*nb1)), and so are the
-// TMEM accumulators (D1/D2 of stage s at columns s*128 / s*128+64), so that the TMA loads, the
+// TMEM buffers (stage s: D1 at column s*192, hidden at +64, D2 at +128), so that the TMA loads, the
 // gathers and the first GEMM of tile i+1 overlap the epilogue of tile i.
 #include <cuda.h>
 #include <stdlib.h>
@@ -190,6 +192,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TMEM (lane = row, column = k; 32-bit elements), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -286,7 +308,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(256u)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -356,7 +378,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (ready) {
             tc_fence_after();
             NLAM_DBG(3, it);
-            const uint32_t d1 = tmem_base + st * 128;
+            const uint32_t d1 = tmem_base + st * 192;
             for (int j = 0; j < p.nb1; ++j) {
               // A block j: TMA blocks come from the stage, produced blocks (edge gathers) are fixed
               int blk;
@@ -380,14 +402,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (mbar_test(bar_hb_full, (uint32_t)(it & 1))) {
             tc_fence_after();
             NLAM_DBG(4, it);
-            const uint32_t d2 = tmem_base + st * 128 + 64;
+            const uint32_t ht = tmem_base + st * 192 + 64;  // hidden activations (A operand in TMEM)
+            const uint32_t d2 = tmem_base + st * 192 + 128;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint64_t ad = umma_desc(sbase + OFF_HB + j * A_BLOCK + k * 32);
                 uint64_t bd = umma_desc(sbase + OFF_W2 + j * W_BLOCK + k * 32);
-                umma_tf32(d2, ad, bd, idesc2, (uint32_t)((j | k) != 0));
+                umma_tf32_ts(d2, ht + (uint32_t)(j * 32 + k * 8), bd, idesc2, (uint32_t)((j | k) != 0));
               }
             }
             umma_commit(bar_d2_full + 8 * st);
@@ -406,6 +428,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     // =============================== producers ===============================
     if (has_prod) {
       const int pt = tid - EPI_THREADS;  // 0..127
+      if (!p.mode_edge) {
+        for (int cc = p.k_real; cc < p.nb1 * 32; ++cc)
+          *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = 0.f;
+      }
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int b = w / p.n_tiles;
@@ -437,25 +463,34 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           }
           cp_async_wait_all();
         } else {
-          // generic concatenation of narrow inputs: element-wise, zero padded to nb1*32 columns
-          const int kpad = p.nb1 * 32;
-          const long long row0 = (long long)t * BM;
-          for (int i = pt; i < BM * kpad; i += PROD_THREADS) {
-            const int row = i / kpad, col = i - row * kpad;
-            float v = 0.f;
-            const long long gr = row0 + row;
-            if (gr < p.n_rows && col < p.k_real) {
-              int c = col;
+          // generic concatenation of narrow inputs (e.g. prev | prev_prev | forcing | static grid
+          // features, graph/base.py:275-283): producer thread pt owns tile row pt and walks its row
+          // of every source; the zero padding up to nb1*32 columns was written once before the loop
+          const long long gr = (long long)t * BM + pt;
+          if (gr < p.n_rows) {
+            int col = 0;
 #pragma unroll
-              for (int s = 0; s < NLAM_MAX_SRC; ++s) {
-                if (s < p.n_elem) {
-                  if (c >= 0 && c < p.edim[s]) v = p.esrc[s][(long long)b * p.ebs[s] + gr * p.edim[s] + c];
-                  c -= p.edim[s];
+            for (int sidx = 0; sidx < NLAM_MAX_SRC; ++sidx) {
+              if (sidx < p.n_elem) {
+                const int d = p.edim[sidx];
+                const float* src = p.esrc[sidx] + (long long)b * p.ebs[sidx] + gr * d;
+                int c = 0;
+                for (; c + 4 <= d; c += 4) {
+                  const float v0 = __ldg(src + c), v1 = __ldg(src + c + 1), v2 = __ldg(src + c + 2), v3 = __ldg(src + c + 3);
+                  const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int cc = col + c + u;
+                    *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = vv[u];
+                  }
                 }
+                for (; c < d; ++c) {
+                  const int cc = col + c;
+                  *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = __ldg(src + c);
+                }
+                col += d;
               }
             }
-            const uint32_t off = OFF_A + (col >> 5) * A_BLOCK + swz(row, (col & 31) >> 2) + (col & 3) * 4;
-            *reinterpret_cast<float*>(smem + off) = v;
           }
         }
         fence_proxy_async();
@@ -495,8 +530,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
-      const uint32_t tmem_d1 = tmem_base + st * 128;
-      const uint32_t tmem_d2 = tmem_d1 + 64;
+      const uint32_t tmem_d1 = tmem_base + st * 192;
+      const uint32_t tmem_ht = tmem_d1 + 64;
+      const uint32_t tmem_d2 = tmem_d1 + 128;
       const int b = w / p.n_tiles;
       const int row0 = meta.x, nrows = meta.y, r0 = meta.z, nrec = meta.w;
       const int cur_lp = lp_val;
@@ -512,20 +548,15 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       if (tid == 0) NLAM_DBG(6, it);
       float v[16];
       tmem_ld16(tmem_d1 + t_lane + c0, v);
-      {
-        uint8_t* hb = smem + OFF_HB + blk * A_BLOCK + rsw;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float4 o;
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c0 + 4 * k));
-          o.x = silu_fast(v[4 * k + 0] + bb.x);
-          o.y = silu_fast(v[4 * k + 1] + bb.y);
-          o.z = silu_fast(v[4 * k + 2] + bb.z);
-          o.w = silu_fast(v[4 * k + 3] + bb.w);
-          *reinterpret_cast<float4*>(hb + (((ch0 + k) ^ rx) << 4)) = o;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c0 + 4 * k));
+        v[4 * k + 0] = silu_fast(v[4 * k + 0] + bb.x);
+        v[4 * k + 1] = silu_fast(v[4 * k + 1] + bb.y);
+        v[4 * k + 2] = silu_fast(v[4 * k + 2] + bb.z);
+        v[4 * k + 3] = silu_fast(v[4 * k + 3] + bb.w);
       }
-      fence_proxy_async();
+      tmem_st16(tmem_ht + t_lane + c0, v);  // hidden stays in TMEM: A operand of the second GEMM
       tc_fence_before();
       mbar_arrive(bar_hb_full);
       if (tid == 0) NLAM_DBG(7, it);
@@ -690,7 +721,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   if (warp == EPI_WARPS + 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

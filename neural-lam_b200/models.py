@@ -460,3 +460,32 @@ class ARForecaster(nn.Module):
             bufs["prev_prev"].copy_(bufs["prev"])
             bufs["prev"].copy_(bufs["out"])
         return out
+
+    @torch.no_grad()
+    def rollout_from_host(self, init_states, forcing_features, boundary_states, out=None):
+        """Inference rollout with HOST tensors (ideally pinned): every AR step copies that step's
+        forcing + boundary states host->device, replays the captured step graph and copies the
+        predicted state device->host, all stream-ordered (H2D of step i+1 is enqueued behind the
+        replay of step i; nothing synchronises until the end).  Shapes as in ``forward``; returns
+        the (B,T,G,d) prediction on the host (``out`` if given)."""
+        B, T = forcing_features.shape[0], forcing_features.shape[1]
+        dev = self.boundary_mask.device
+        if self._graph is None or self._graph[0] != B:
+            self.capture(B)
+        _, graph, bufs = self._graph
+        if out is None:
+            out = torch.empty(B, T, *init_states.shape[2:], dtype=torch.float32, pin_memory=True)
+        for b in range(B):
+            bufs["prev_prev"][b].copy_(init_states[b, 0], non_blocking=True)
+            bufs["prev"][b].copy_(init_states[b, 1], non_blocking=True)
+        for i in range(T):
+            for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
+                bufs["forcing"][b].copy_(forcing_features[b, i], non_blocking=True)
+                bufs["boundary"][b].copy_(boundary_states[b, i], non_blocking=True)
+            graph.replay()
+            for b in range(B):
+                out[b, i].copy_(bufs["out"][b], non_blocking=True)
+            bufs["prev_prev"].copy_(bufs["prev"])
+            bufs["prev"].copy_(bufs["out"])
+        torch.cuda.current_stream(dev).synchronize()
+        return out
