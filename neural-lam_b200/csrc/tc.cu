@@ -13,13 +13,15 @@
 //     a = up to two 64-wide row blocks by TMA (e.g. [rec | aggr]) or a generic concatenation
 //     of narrow inputs (grid features 17|17|18|4); optional residual, optional LayerNorm.
 //
-// Warp roles (704 threads, 1 CTA / SM, persistent over (batch, tile) work items):
-//   warps 0-15  epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/SiLU/LayerNorm/residual,
-//               segmented reduction, coalesced stores.  warp%4 selects the TMEM lane quarter,
-//               warp/4 the 16-column quarter.
-//   warps 16-19 producers: index-driven gathers (cp.async 16 B, manual 128B swizzle)
-//   warp 20     TMEM allocation + single-thread tcgen05.mma issue
-//   warp 21     TMA loads (weights once, A tiles per work item)
+// Warp roles (832 threads, 1 CTA / SM, persistent over (batch, tile) work items):
+//   warps 0-15  epilogue 2: D2 from TMEM (tcgen05.ld 32x32b), bias / LayerNorm / residual,
+//               segmented reduction, TMA stores.  warp%4 selects the TMEM lane quarter (hardware
+//               restriction), warp/4 the 16-column quarter.
+//   warps 16-19 epilogue 1: D1 -> bias + SiLU -> hidden, TMEM to TMEM (thread = tile row); its own
+//               group so that tile i+1's first epilogue overlaps tile i's second epilogue
+//   warps 20-23 producers: index-driven gathers (cp.async 16 B, manual 128B swizzle)
+//   warp 24     TMEM allocation + single-thread tcgen05.mma issue
+//   warp 25     TMA loads (weights once, A tiles per work item)
 //
 // The hidden activations never touch shared memory: the first epilogue writes SiLU(D1+b1) back to
 // TMEM (tcgen05.st) and the second GEMM reads its A operand from TMEM (tcgen05.mma "TS" form).
@@ -38,10 +40,15 @@
 
 namespace nlam {
 
-constexpr int TC_THREADS = 704;
+constexpr int TC_THREADS = 832;
 constexpr int EPI_THREADS = 512;
 constexpr int EPI_WARPS = EPI_THREADS / 32;
 constexpr int PROD_THREADS = 128;
+constexpr int E1_THREADS = 128;
+constexpr int W_E1 = EPI_WARPS;        // first warp of the epilogue-1 group (4 warps)
+constexpr int W_PROD = EPI_WARPS + 4;   // producers (4 warps)
+constexpr int W_MMA = EPI_WARPS + 8;
+constexpr int W_TMA = EPI_WARPS + 9;
 constexpr int BM = 128;
 constexpr uint32_t A_BLOCK = 16384;  // 128 rows x 128 B
 constexpr uint32_t W_BLOCK = 8192;   // 64 rows x 128 B
@@ -212,6 +219,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -274,15 +297,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const uint32_t bar_w = mb + 0;
   const uint32_t bar_a_gat_full = mb + 8;
   const uint32_t bar_a_free_g = mb + 16;
-  const uint32_t bar_hb_full = mb + 24;
   // stage-indexed (add 8*s)
+  const uint32_t bar_hb_full = mb + 96;
   const uint32_t bar_a_tma_full = mb + 32;
   const uint32_t bar_epi_done = mb + 48;
   const uint32_t bar_d1_full = mb + 64;
   const uint32_t bar_d2_full = mb + 80;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 96);
-  float* ln_x = reinterpret_cast<float*>(smem + OFF_MISC + 128);   // [4 column quarters][128 rows]
-  int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 128 + 2048);  // local CSR offsets, <= 129 entries
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 120);
+  int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 128);  // local CSR offsets, <= 129 entries
 
   if ((sbase & 1023u) != 0) {
     if (tid == 0) printf("nlam tc kernel: dynamic shared memory not 1024-byte aligned\n");
@@ -292,17 +314,17 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const bool has_tma_a = (p.a0_blocks + p.a1_blocks) > 0;
   const bool has_prod = p.mode_edge || p.n_elem > 0;
 
-  if (warp == EPI_WARPS + 4) {
+  if (warp == W_MMA) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
       mbar_init(bar_a_gat_full, PROD_THREADS);
       mbar_init(bar_a_free_g, 1);
-      mbar_init(bar_hb_full, EPI_THREADS);
       for (int st = 0; st < 2; ++st) {
         mbar_init(bar_a_tma_full + 8 * st, 1);
         mbar_init(bar_epi_done + 8 * st, 1);
         mbar_init(bar_d1_full + 8 * st, 1);
         mbar_init(bar_d2_full + 8 * st, 1);
+        mbar_init(bar_hb_full + 8 * st, E1_THREADS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -312,7 +334,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == EPI_WARPS + 5 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     if (p.a0_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -328,7 +350,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   const int n_work = p.n_tiles * p.B;  // host guarantees < 2^31
 
-  if (warp == EPI_WARPS + 5) {
+  if (warp == W_TMA) {
     // =============================== TMA loader ===============================
     if (lane == 0) {
       const uint32_t w2_block_bytes = (uint32_t)p.n2 * 128u;
@@ -354,7 +376,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == EPI_WARPS + 4) {
+  } else if (warp == W_MMA) {
     // =============================== MMA issuer ===============================
     // Software pipelined: GEMM1 of tile i+1 is issued as soon as its operands have landed,
     // GEMM2 of tile i as soon as the epilogue has produced the hidden activations.
@@ -399,7 +421,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
         if (g2 < g1) {
           const int it = g2, st = it & 1;
-          if (mbar_test(bar_hb_full, (uint32_t)(it & 1))) {
+          if (mbar_test(bar_hb_full + 8 * st, (uint32_t)((it >> 1) & 1))) {
             tc_fence_after();
             NLAM_DBG(4, it);
             const uint32_t ht = tmem_base + st * 192 + 64;  // hidden activations (A operand in TMEM)
@@ -424,10 +446,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= EPI_WARPS) {
+  } else if (warp >= W_PROD) {
     // =============================== producers ===============================
     if (has_prod) {
-      const int pt = tid - EPI_THREADS;  // 0..127
+      const int pt = tid - W_PROD * 32;  // 0..127
       if (!p.mode_edge) {
         for (int cc = p.k_real; cc < p.nb1 * 32; ++cc)
           *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = 0.f;
@@ -498,8 +520,43 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         mbar_arrive(bar_a_gat_full);
       }
     }
+  } else if (warp >= W_E1) {
+    // =============================== epilogue 1 (warps 16-19) ===============================
+    // hidden = SiLU(D1 + b1), TMEM -> registers -> TMEM (A operand of the second GEMM).  Runs on
+    // its own warp group so that it overlaps the second epilogue of the previous tile.
+    const int q = warp & 3;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t sph = (uint32_t)((it >> 1) & 1);
+      const uint32_t tmem_d1 = tmem_base + st * 192;
+      const uint32_t tmem_ht = tmem_d1 + 64;
+      if (tid == W_E1 * 32) NLAM_DBG(5, it);
+      mbar_wait(bar_d2_full + 8 * st, sph ^ 1);  // GEMM2 of tile it-2 has consumed this hidden buffer
+      mbar_wait(bar_d1_full + 8 * st, sph);
+      tc_fence_after();
+      if (tid == W_E1 * 32) NLAM_DBG(6, it);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[16];
+        tmem_ld16(tmem_d1 + t_lane + cc * 16, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + cc * 16 + 4 * k));
+          v[4 * k + 0] = silu_fast(v[4 * k + 0] + bb.x);
+          v[4 * k + 1] = silu_fast(v[4 * k + 1] + bb.y);
+          v[4 * k + 2] = silu_fast(v[4 * k + 2] + bb.z);
+          v[4 * k + 3] = silu_fast(v[4 * k + 3] + bb.w);
+        }
+        tmem_st16(tmem_ht + t_lane + cc * 16, v);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_hb_full + 8 * st);
+      if (tid == W_E1 * 32) NLAM_DBG(7, it);
+    }
   } else {
-    // =============================== epilogue (warps 0-15) ===============================
+    // =============================== epilogue 2 (warps 0-15) ===============================
     // thread = (tile row, 16-column quarter): warp%4 selects the TMEM lane quarter (hardware
     // restriction of tcgen05.ld), warp/4 the column quarter.
     const int q = warp & 3;
@@ -521,45 +578,30 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       return make_int4((int)r0, (int)min((long long)BM, p.n_rows - r0), 0, 0);
     };
     int4 meta = make_int4(0, 0, 0, 0);
+    int4 meta_n = meta;
     int lp_val = 0;
     if ((int)blockIdx.x < n_work) {
       meta = load_meta(blockIdx.x);
+      meta_n = meta;
+      if ((int)(blockIdx.x + gridDim.x) < n_work) meta_n = load_meta(blockIdx.x + gridDim.x);
       if (p.mode_edge && tid <= meta.w) lp_val = __ldg(p.rowptr + meta.z + tid) - meta.x;
     }
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t sph = (uint32_t)((it >> 1) & 1);
-      const uint32_t tmem_d1 = tmem_base + st * 192;
-      const uint32_t tmem_ht = tmem_d1 + 64;
-      const uint32_t tmem_d2 = tmem_d1 + 128;
+      const uint32_t tmem_d2 = tmem_base + st * 192 + 128;
       const int b = w / p.n_tiles;
       const int row0 = meta.x, nrows = meta.y, r0 = meta.z, nrec = meta.w;
       const int cur_lp = lp_val;
-      // prefetch the next tile's metadata (consumed at the end of this iteration)
+      // metadata is prefetched two tiles ahead so that the dependent CSR-offset load of the next
+      // tile never waits on it
       const int wn = w + (int)gridDim.x;
-      int4 meta_n = meta;
-      if (wn < n_work) meta_n = load_meta(wn);
+      const int wnn = wn + (int)gridDim.x;
+      int4 meta_nn = meta_n;
+      if (wnn < n_work) meta_nn = load_meta(wnn);
 
-      // ---- E1: hidden = SiLU(D1 + b1) -> HB (UMMA A operand layout) ----
-      if (tid == 0) NLAM_DBG(5, it);
-      mbar_wait(bar_d1_full + 8 * st, sph);
-      tc_fence_after();
-      if (tid == 0) NLAM_DBG(6, it);
       float v[16];
-      tmem_ld16(tmem_d1 + t_lane + c0, v);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c0 + 4 * k));
-        v[4 * k + 0] = silu_fast(v[4 * k + 0] + bb.x);
-        v[4 * k + 1] = silu_fast(v[4 * k + 1] + bb.y);
-        v[4 * k + 2] = silu_fast(v[4 * k + 2] + bb.z);
-        v[4 * k + 3] = silu_fast(v[4 * k + 3] + bb.w);
-      }
-      tmem_st16(tmem_ht + t_lane + c0, v);  // hidden stays in TMEM: A operand of the second GEMM
-      tc_fence_before();
-      mbar_arrive(bar_hb_full);
-      if (tid == 0) NLAM_DBG(7, it);
       if (p.mode_edge) {
         if (tid <= nrec) lp[tid] = cur_lp;  // the previous tile's reduction has passed its final barrier
         if (wn < n_work && tid <= meta_n.w) lp_val = __ldg(p.rowptr + meta_n.z + tid) - meta_n.x;
@@ -587,32 +629,33 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (c0 + i < p.nout) v[i] += __ldg(p.b2 + c0 + i);
       }
       if (p.gamma) {
-        // two-pass LayerNorm over 64 columns split across the four column quarters
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s += v[i];
-        ln_x[cq * BM + row] = s;
-        named_bar_sync(lnbar, 128);
-        const float mu = (ln_x[row] + ln_x[BM + row] + ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
-        float sq = 0.f;
+        // LayerNorm over 64 columns split across the four column quarters: each thread parks its
+        // partial (sum, sum of squares) in two spare TMEM columns of its lane, one barrier scoped to
+        // the 4 warps of the lane quarter, then every thread reads the 4 pairs of its row back.
+        float s = 0.f, sq = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          v[i] -= mu;
-          sq += v[i] * v[i];
+          s += v[i];
+          sq = fmaf(v[i], v[i], sq);
         }
-        named_bar_sync(lnbar, 128);  // the quarter has read the sums; the array is reused
-        ln_x[cq * BM + row] = sq;
+        const uint32_t lnx = tmem_base + 384 + t_lane;
+        tmem_st2(lnx + 2 * cq, s, sq);
+        tc_fence_before();
         named_bar_sync(lnbar, 128);
-        const float var = (ln_x[row] + ln_x[BM + row] + ln_x[2 * BM + row] + ln_x[3 * BM + row]) * (1.0f / 64.0f);
-        const float rstd = rsqrtf(var + p.eps);
+        tc_fence_after();
+        float st8[8];
+        tmem_ld8(lnx, st8);
+        const float mu = (st8[0] + st8[2] + st8[4] + st8[6]) * (1.0f / 64.0f);
+        const float ex2 = (st8[1] + st8[3] + st8[5] + st8[7]) * (1.0f / 64.0f);
+        const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4 * k));
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * k));
-          v[4 * k + 0] = v[4 * k + 0] * rstd * g4.x + b4.x;
-          v[4 * k + 1] = v[4 * k + 1] * rstd * g4.y + b4.y;
-          v[4 * k + 2] = v[4 * k + 2] * rstd * g4.z + b4.z;
-          v[4 * k + 3] = v[4 * k + 3] * rstd * g4.w + b4.w;
+          v[4 * k + 0] = (v[4 * k + 0] - mu) * rstd * g4.x + b4.x;
+          v[4 * k + 1] = (v[4 * k + 1] - mu) * rstd * g4.y + b4.y;
+          v[4 * k + 2] = (v[4 * k + 2] - mu) * rstd * g4.z + b4.z;
+          v[4 * k + 3] = (v[4 * k + 3] - mu) * rstd * g4.w + b4.w;
         }
       }
       if (tid == 0) NLAM_DBG(9, it);
@@ -712,6 +755,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         mbar_arrive(bar_epi_done + 8 * st);
       }
       meta = meta_n;
+      meta_n = meta_nn;
     }
     if (tid == 0) bulk_wait0();  // all output stores complete before the CTA retires
   }
@@ -720,7 +764,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == EPI_WARPS + 4) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }

@@ -463,11 +463,12 @@ class ARForecaster(nn.Module):
 
     @torch.no_grad()
     def rollout_from_host(self, init_states, forcing_features, boundary_states, out=None):
-        """Inference rollout with HOST tensors (ideally pinned): every AR step copies that step's
+        """Inference rollout with HOST tensors (ideally pinned).  Every AR step copies that step's
         forcing + boundary states host->device, replays the captured step graph and copies the
-        predicted state device->host, all stream-ordered (H2D of step i+1 is enqueued behind the
-        replay of step i; nothing synchronises until the end).  Shapes as in ``forward``; returns
-        the (B,T,G,d) prediction on the host (``out`` if given)."""
+        predicted state device->host.  The PCIe transfers run on their own streams, double
+        buffered, so that H2D of step i+1 and D2H of step i-1 overlap the kernels of step i;
+        nothing synchronises with the host until the end.  Shapes as in ``forward``; returns the
+        (B,T,G,d) prediction on the host (``out`` if given)."""
         B, T = forcing_features.shape[0], forcing_features.shape[1]
         dev = self.boundary_mask.device
         if self._graph is None or self._graph[0] != B:
@@ -475,17 +476,58 @@ class ARForecaster(nn.Module):
         _, graph, bufs = self._graph
         if out is None:
             out = torch.empty(B, T, *init_states.shape[2:], dtype=torch.float32, pin_memory=True)
+        if getattr(self, "_io", None) is None or self._io["B"] != B:
+            self._io = {
+                "B": B, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
+                "forc": [torch.empty_like(bufs["forcing"]) for _ in range(2)],
+                "bnd": [torch.empty_like(bufs["boundary"]) for _ in range(2)],
+                "out": [torch.empty_like(bufs["out"]) for _ in range(2)],
+            }
+        io = self._io
+        main = torch.cuda.current_stream(dev)
+        s_in, s_out = io["s_in"], io["s_out"]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
+
+        def h2d(i):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(in_free[k])
+                for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
+                    io["forc"][k][b].copy_(forcing_features[b, i], non_blocking=True)
+                    io["bnd"][k][b].copy_(boundary_states[b, i], non_blocking=True)
+                in_ready[k].record(s_in)
+
         for b in range(B):
             bufs["prev_prev"][b].copy_(init_states[b, 0], non_blocking=True)
             bufs["prev"][b].copy_(init_states[b, 1], non_blocking=True)
+        h2d(0)
         for i in range(T):
-            for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
-                bufs["forcing"][b].copy_(forcing_features[b, i], non_blocking=True)
-                bufs["boundary"][b].copy_(boundary_states[b, i], non_blocking=True)
+            k = i & 1
+            if i + 1 < T:
+                h2d(i + 1)
+            main.wait_event(in_ready[k])
+            bufs["forcing"].copy_(io["forc"][k])
+            bufs["boundary"].copy_(io["bnd"][k])
+            in_free[k].record(main)
             graph.replay()
-            for b in range(B):
-                out[b, i].copy_(bufs["out"][b], non_blocking=True)
+            if i >= 2:
+                main.wait_event(out_free[k])
+            io["out"][k].copy_(bufs["out"])
+            out_ready[k].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(out_ready[k])
+                for b in range(B):
+                    out[b, i].copy_(io["out"][k][b], non_blocking=True)
+                out_free[k].record(s_out)
             bufs["prev_prev"].copy_(bufs["prev"])
             bufs["prev"].copy_(bufs["out"])
-        torch.cuda.current_stream(dev).synchronize()
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+        main.synchronize()
         return out

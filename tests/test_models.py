@@ -107,6 +107,14 @@ def test_step_and_rollout_match_oracle_fp32(kind):
     # tolerance: fp32 kernels vs fp32 oracle after 2 AR steps through up to 16 stacked layers
     torch.testing.assert_close(got.cpu(), want, rtol=2e-4, atol=2e-4)
     torch.testing.assert_close(got_graphed.cpu(), got.cpu(), rtol=1e-6, atol=1e-6)
+    # public host-buffer API (pinned in, pinned out, PCIe copies overlapped with the kernels)
+    T5 = 5
+    forc5, bnd5 = torch.randn(B, T5, G, 6, generator=gen).pin_memory(), torch.randn(B, T5, G, 5, generator=gen).pin_memory()
+    with torch.no_grad():
+        host = fc.rollout_from_host(init.pin_memory(), forc5, bnd5)
+        ref5 = fc.rollout_graphed(init.cuda(), forc5.cuda(), bnd5.cuda())
+    assert not host.is_cuda
+    torch.testing.assert_close(host, ref5.cpu(), rtol=0, atol=0)
     err64 = (got.cpu().double() - want64).abs().max().item()
     ref64 = (want.double() - want64).abs().max().item()
     assert err64 < max(10 * ref64, 2e-4), (err64, ref64)
