@@ -166,6 +166,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -217,6 +222,19 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "tcgen05.wait::st.sync.aligned;"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
@@ -373,6 +391,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             tma_load_3d(abase + j * A_BLOCK, &tmA0, full, 32 * j, row0, p.a0_batched ? b : 0);
           for (int j = 0; j < p.a1_blocks; ++j)
             tma_load_3d(abase + (p.a0_blocks + j) * A_BLOCK, &tmA1, full, 32 * j, row0, p.a1_batched ? b : 0);
+          // pull the tile two iterations ahead into L2 so that its TMA load is an L2 hit
+          const int w2 = w + 2 * (int)gridDim.x;
+          if (w2 < n_work) {
+            const int b2 = w2 / p.n_tiles, t2 = w2 - b2 * p.n_tiles;
+            const int r2 = p.mode_edge ? p.tile_e0[t2] : t2 * BM;
+            for (int j = 0; j < p.a0_blocks; ++j) tma_prefetch_3d(&tmA0, 32 * j, r2, p.a0_batched ? b2 : 0);
+            for (int j = 0; j < p.a1_blocks; ++j) tma_prefetch_3d(&tmA1, 32 * j, r2, p.a1_batched ? b2 : 0);
+          }
         }
       }
     }
@@ -454,6 +480,16 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         for (int cc = p.k_real; cc < p.nb1 * 32; ++cc)
           *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = 0.f;
       }
+      int pf_ne = 0;
+      int pf_idx[2] = {0, 0};
+      if (p.mode_edge && (int)blockIdx.x < n_work) {
+        const int t0 = (int)blockIdx.x % p.n_tiles;
+        const int e00 = p.tile_e0[t0];
+        pf_ne = (int)min((long long)BM, p.n_rows - e00);
+        const int my_row = (pt >> 5) * 32 + lane;
+        pf_idx[0] = (my_row < pf_ne) ? __ldg(p.gidx[0] + e00 + my_row) : 0;
+        pf_idx[1] = (my_row < pf_ne) ? __ldg(p.gidx[1] + e00 + my_row) : 0;
+      }
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int b = w / p.n_tiles;
@@ -461,17 +497,15 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
         if (pt == 0) NLAM_DBG(1, it);
         if (p.mode_edge) {
-          const int e0 = p.tile_e0[t];
-          const int ne = (int)min((long long)BM, p.n_rows - e0);  // whole window, clipped at the end
-          // each warp owns 32 tile rows; a half-warp copies one 256-byte row per instruction
+          // each warp owns 32 tile rows; a half-warp copies one 256-byte row per instruction.  The
+          // row indices of this tile were loaded while waiting (prefetched in the previous iteration).
+          const int ne = pf_ne;
           const int pw = pt >> 5;
-          const int my_row = pw * 32 + lane;
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            int my_idx = 0;
-            if (my_row < ne) my_idx = p.gidx[s][e0 + my_row];
-            const float* base = p.gsrc[s] + (long long)b * p.gbs[s];
-            const uint32_t blk0 = sbase + OFF_A + (2 + 2 * s) * A_BLOCK;
+          for (int sidx = 0; sidx < 2; ++sidx) {
+            const int my_idx = pf_idx[sidx];
+            const float* base = p.gsrc[sidx] + (long long)b * p.gbs[sidx];
+            const uint32_t blk0 = sbase + OFF_A + (2 + 2 * sidx) * A_BLOCK;
 #pragma unroll 4
             for (int i = 0; i < 16; ++i) {
               const int rl = 2 * i + (lane >> 4);  // row within the warp's 32
@@ -481,6 +515,18 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               const float* g = base + (long long)src_row * 64 + ch * 4;
               const uint32_t dst = blk0 + (ch >> 3) * A_BLOCK + swz(row, ch & 7);
               if (row < ne) cp_async_16(dst, g);
+            }
+          }
+          // prefetch the indices of the next tile while the copies are in flight
+          {
+            const int wn = w + (int)gridDim.x;
+            if (wn < n_work) {
+              const int tn = wn % p.n_tiles;
+              const int e0n = p.tile_e0[tn];
+              pf_ne = (int)min((long long)BM, p.n_rows - e0n);
+              const int my_row = pw * 32 + lane;
+              pf_idx[0] = (my_row < pf_ne) ? __ldg(p.gidx[0] + e0n + my_row) : 0;
+              pf_idx[1] = (my_row < pf_ne) ? __ldg(p.gidx[1] + e0n + my_row) : 0;
             }
           }
           cp_async_wait_all();
@@ -538,18 +584,18 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       tc_fence_after();
       if (tid == W_E1 * 32) NLAM_DBG(6, it);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float v[16];
-        tmem_ld16(tmem_d1 + t_lane + cc * 16, v);
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        tmem_ld32(tmem_d1 + t_lane + cc * 32, v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + cc * 16 + 4 * k));
+        for (int k = 0; k < 8; ++k) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + cc * 32 + 4 * k));
           v[4 * k + 0] = silu_fast(v[4 * k + 0] + bb.x);
           v[4 * k + 1] = silu_fast(v[4 * k + 1] + bb.y);
           v[4 * k + 2] = silu_fast(v[4 * k + 2] + bb.z);
           v[4 * k + 3] = silu_fast(v[4 * k + 3] + bb.w);
         }
-        tmem_st16(tmem_ht + t_lane + cc * 16, v);
+        tmem_st32(tmem_ht + t_lane + cc * 32, v);
       }
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * st);
