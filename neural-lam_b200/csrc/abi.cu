@@ -57,7 +57,9 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   const int64_t aggr_bs = (int64_t)g->n_rec * H;
 
   if (use_tc) {
-    int rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st);
+    // rows of the sender tensor: known exactly when the batches are dense, else at least n_send
+    const int64_t send_rows = (B > 1 && send_bs > 0) ? send_bs / H : g->n_send;
+    int rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
     if (rc) return rc;
   } else {
     NLAM_REQUIRE(workspace && ws_bytes >= msg_bytes, NLAM_E_WORKSPACE, "nlam_inet_fwd: workspace too small");

@@ -77,5 +77,5 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
 bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags);
 int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs,
             const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out,
-            float* aggr_out, int B, int flags, cudaStream_t stream);
+            float* aggr_out, int B, int flags, cudaStream_t stream, int64_t send_rows);
 }  // namespace nlam

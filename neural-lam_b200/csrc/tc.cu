@@ -70,6 +70,8 @@ struct TcParams {
   const float* gsrc[2];
   long long gbs[2];
   const int32_t* gidx[2];
+  int use_g4;      // gather with TMA tile::gather4 (one instruction per 4 rows x 32 columns)
+  int g4_rows[2];  // rows of one batch in the gather4 tensor maps (0 for batch-broadcast sources)
   // generic element-wise sources (row mode): concatenated into blocks [0, nb1)
   int n_elem;
   const float* esrc[NLAM_MAX_SRC];
@@ -111,17 +113,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware until the phase completes or the time hint expires
   uint32_t done = 0;
   uint32_t spins = 0;
-  while (!done) {
+  while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000u)
         : "memory");
-    if (!done && ++spins > (1u << 24)) {  // bounded: a protocol bug must not hang the GPU
+    if (done) break;
+    if (++spins > (1u << 20)) {  // bounded: a protocol bug must not hang the GPU
       printf("nlam tc kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
       __trap();
@@ -146,16 +150,46 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+// One warp of a warp group polls the mbarrier; the others block on a hardware named barrier, which
+// costs no issue slots (26 warps all polling measurably slowed the working warps down).
+__device__ __forceinline__ void group_wait(bool leader, uint32_t bar, uint32_t parity, int bar_id, int nthreads) {
+  if (leader) mbar_wait(bar, parity);
+  named_bar_sync(bar_id, nthreads);
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+// L2 eviction policies: the streamed edge tiles (hundreds of MB per layer at the bench batch) must
+// not push the small, heavily re-read node rows (gather sources) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+      : "memory");
+}
+// TMA tile::gather4: 4 rows (arbitrary row indices) x 32 columns -> 4 consecutive 128-byte smem rows
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -171,8 +205,8 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
                ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -304,7 +338,8 @@ __device__ __forceinline__ float silu_fast(float x) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-              const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
+              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmG0,
+              const __grid_constant__ CUtensorMap tmG1, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x;
@@ -315,6 +350,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const uint32_t bar_w = mb + 0;
   const uint32_t bar_a_gat_full = mb + 8;
   const uint32_t bar_a_free_g = mb + 16;
+  const uint32_t bar_a_g4_full = mb + 24;  // gather4 mode: 1 arrival + 64 KB of TMA transactions
   // stage-indexed (add 8*s)
   const uint32_t bar_hb_full = mb + 96;
   const uint32_t bar_a_tma_full = mb + 32;
@@ -337,6 +373,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       mbar_init(bar_w, 1);
       mbar_init(bar_a_gat_full, PROD_THREADS);
       mbar_init(bar_a_free_g, 1);
+      mbar_init(bar_a_g4_full, 1);
       for (int st = 0; st < 2; ++st) {
         mbar_init(bar_a_tma_full + 8 * st, 1);
         mbar_init(bar_epi_done + 8 * st, 1);
@@ -358,6 +395,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (p.a0_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     if (p.a1_blocks) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     if (p.out && p.nout == 64) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    if (p.use_g4) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG0) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG1) : "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -376,6 +417,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       for (int j = 0; j < p.nb1; ++j) tma_load_2d(sbase + OFF_W1 + j * W_BLOCK, &tmW1, bar_w, 32 * j, 0);
       for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * W_BLOCK, &tmW2, bar_w, 32 * j, 0);
       if (has_tma_a) {
+        const uint64_t pol_stream = policy_evict_first();
         int it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
           const int b = w / p.n_tiles;
@@ -388,9 +430,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           NLAM_DBG(0, it);
           mbar_expect_tx(full, (uint32_t)(p.a0_blocks + p.a1_blocks) * A_BLOCK);
           for (int j = 0; j < p.a0_blocks; ++j)
-            tma_load_3d(abase + j * A_BLOCK, &tmA0, full, 32 * j, row0, p.a0_batched ? b : 0);
+            tma_load_3d(abase + j * A_BLOCK, &tmA0, full, 32 * j, row0, p.a0_batched ? b : 0, pol_stream);
           for (int j = 0; j < p.a1_blocks; ++j)
-            tma_load_3d(abase + (p.a0_blocks + j) * A_BLOCK, &tmA1, full, 32 * j, row0, p.a1_batched ? b : 0);
+            tma_load_3d(abase + (p.a0_blocks + j) * A_BLOCK, &tmA1, full, 32 * j, row0, p.a1_batched ? b : 0, pol_stream);
           // pull the tile two iterations ahead into L2 so that its TMA load is an L2 hit
           const int w2 = w + 2 * (int)gridDim.x;
           if (w2 < n_work) {
@@ -412,6 +454,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       int n_my = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
       mbar_wait(bar_w, 0);
+      const uint64_t desc_a0 = umma_desc(sbase + OFF_A);
+      const uint64_t desc_w1 = umma_desc(sbase + OFF_W1);
+      const uint64_t desc_w2 = umma_desc(sbase + OFF_W2);
       int g1 = 0, g2 = 0;
       uint32_t idle = 0;
       while (g2 < n_my) {
@@ -422,7 +467,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           bool ready = true;
           if (has_tma_a) ready = mbar_test(bar_a_tma_full + 8 * st, sph);
           else ready = mbar_test(bar_epi_done + 8 * st, sph ^ 1);  // accumulators of tile it-2 drained
-          if (ready && has_prod) ready = mbar_test(bar_a_gat_full, (uint32_t)(it & 1));
+          if (ready && has_prod) ready = mbar_test(p.use_g4 ? bar_a_g4_full : bar_a_gat_full, (uint32_t)(it & 1));
           if (ready) {
             tc_fence_after();
             NLAM_DBG(3, it);
@@ -432,12 +477,12 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               int blk;
               if (p.mode_edge) blk = (j < 2) ? (st ? 6 + j : j) : j;
               else blk = has_tma_a ? (st ? stage_blk1 : 0) + j : j;
+              // descriptor = base + (byte offset >> 4) in the 14-bit start-address field (no carry:
+              // all operands live below 256 KB)
+              const uint64_t ad0 = desc_a0 + (uint64_t)((blk * A_BLOCK) >> 4);
+              const uint64_t bd0 = desc_w1 + (uint64_t)((j * W_BLOCK) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint64_t ad = umma_desc(sbase + OFF_A + blk * A_BLOCK + k * 32);
-                uint64_t bd = umma_desc(sbase + OFF_W1 + j * W_BLOCK + k * 32);
-                umma_tf32(d1, ad, bd, idesc1, (uint32_t)((j | k) != 0));
-              }
+              for (int k = 0; k < 4; ++k) umma_tf32(d1, ad0 + 2 * k, bd0 + 2 * k, idesc1, (uint32_t)((j | k) != 0));
             }
             umma_commit(bar_d1_full + 8 * st);
             if (has_prod) umma_commit(bar_a_free_g);
@@ -455,10 +500,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint64_t bd = umma_desc(sbase + OFF_W2 + j * W_BLOCK + k * 32);
-                umma_tf32_ts(d2, ht + (uint32_t)(j * 32 + k * 8), bd, idesc2, (uint32_t)((j | k) != 0));
-              }
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_ts(d2, ht + (uint32_t)(j * 32 + k * 8), desc_w2 + (uint64_t)((j * W_BLOCK) >> 4) + 2 * k, idesc2,
+                             (uint32_t)((j | k) != 0));
             }
             umma_commit(bar_d2_full + 8 * st);
             ++g2;
@@ -480,6 +524,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         for (int cc = p.k_real; cc < p.nb1 * 32; ++cc)
           *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = 0.f;
       }
+      const uint64_t pol_keep = policy_evict_last();
       int pf_ne = 0;
       int pf_idx[2] = {0, 0};
       if (p.mode_edge && (int)blockIdx.x < n_work) {
@@ -490,13 +535,48 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         pf_idx[0] = (my_row < pf_ne) ? __ldg(p.gidx[0] + e00 + my_row) : 0;
         pf_idx[1] = (my_row < pf_ne) ? __ldg(p.gidx[1] + e00 + my_row) : 0;
       }
+      int pf4[4] = {0, 0, 0, 0};
+      if (p.mode_edge && p.use_g4 && (int)blockIdx.x < n_work) {
+        const int e00 = p.tile_e0[(int)blockIdx.x % p.n_tiles];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          pf4[u] = (4 * (pt & 31) + u < pf_ne) ? __ldg(p.gidx[pt >> 6] + e00 + 4 * (pt & 31) + u) : 0;
+      }
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int b = w / p.n_tiles;
         const int t = w - b * p.n_tiles;
-        mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
+        if (warp == W_PROD) {
+          mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
+          // arm the transaction count before any producer thread can issue its gather
+          if (p.use_g4 && lane == 0) mbar_expect_tx(bar_a_g4_full, 4u * A_BLOCK);
+        }
+        named_bar_sync(8, PROD_THREADS);
         if (pt == 0) NLAM_DBG(1, it);
-        if (p.mode_edge) {
+        if (p.mode_edge && p.use_g4) {
+          // TMA tile::gather4: producer thread pt issues ONE instruction = 4 gathered rows x 32 columns
+          // (512 B, hardware 128B swizzle) of source (pt>>6), column block (pt>>5)&1, row group pt&31.
+          // The four row indices were prefetched during the previous iteration.
+          const int sidx = pt >> 6, jb = (pt >> 5) & 1, grp = pt & 31;
+          const int boff = p.g4_rows[sidx] * b;
+          int r[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) r[u] = (4 * grp + u < pf_ne) ? pf4[u] + boff : 0;  // past the end: any valid row (never stored)
+          tma_gather4(sbase + OFF_A + (2 + 2 * sidx + jb) * A_BLOCK + grp * 512, sidx ? &tmG1 : &tmG0, bar_a_g4_full,
+                      32 * jb, r[0], r[1], r[2], r[3], pol_keep);
+          if (pt == 0) NLAM_DBG(14, it);
+          {
+            const int wn = w + (int)gridDim.x;
+            if (wn < n_work) {
+              const int e0n = p.tile_e0[wn % p.n_tiles];
+              pf_ne = (int)min((long long)BM, p.n_rows - e0n);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pf4[u] = (4 * grp + u < pf_ne) ? __ldg(p.gidx[sidx] + e0n + 4 * grp + u) : 0;
+            }
+          }
+          if (pt == 0) NLAM_DBG(2, it);
+          continue;  // completion is signalled by the TMA transactions themselves
+        } else if (p.mode_edge) {
           // each warp owns 32 tile rows; a half-warp copies one 256-byte row per instruction.  The
           // row indices of this tile were loaded while waiting (prefetched in the previous iteration).
           const int ne = pf_ne;
@@ -514,7 +594,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               const int ch = lane & 15;  // 16-byte chunk of the 256-byte row
               const float* g = base + (long long)src_row * 64 + ch * 4;
               const uint32_t dst = blk0 + (ch >> 3) * A_BLOCK + swz(row, ch & 7);
-              if (row < ne) cp_async_16(dst, g);
+              if (row < ne) cp_async_16(dst, g, pol_keep);
             }
           }
           // prefetch the indices of the next tile while the copies are in flight
@@ -579,8 +659,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const uint32_t tmem_d1 = tmem_base + st * 192;
       const uint32_t tmem_ht = tmem_d1 + 64;
       if (tid == W_E1 * 32) NLAM_DBG(5, it);
-      mbar_wait(bar_d2_full + 8 * st, sph ^ 1);  // GEMM2 of tile it-2 has consumed this hidden buffer
-      mbar_wait(bar_d1_full + 8 * st, sph);
+      if (warp == W_E1) {
+        mbar_wait(bar_d2_full + 8 * st, sph ^ 1);  // GEMM2 of tile it-2 has consumed this hidden buffer
+        mbar_wait(bar_d1_full + 8 * st, sph);
+      }
+      named_bar_sync(7, E1_THREADS);
       tc_fence_after();
       if (tid == W_E1 * 32) NLAM_DBG(6, it);
 #pragma unroll
@@ -654,7 +737,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
 
       // ---- E2: y = D2 + b2, LayerNorm, residual ----
-      mbar_wait(bar_d2_full + 8 * st, sph);
+      group_wait(warp == 0, bar_d2_full + 8 * st, sph, 6, EPI_THREADS);
       tc_fence_after();
       if (tid == 0) NLAM_DBG(8, it);
       const bool active = c0 < p.n2;
@@ -876,7 +959,8 @@ static int num_sms() {
 }
 
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2,
-                  const CUtensorMap& om, const TcParams& p, cudaStream_t st) {
+                  const CUtensorMap& om, const TcParams& p, cudaStream_t st, const CUtensorMap* g0 = nullptr,
+                  const CUtensorMap* g1 = nullptr) {
   static unsigned attr_mask = 0;  // per device
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
@@ -896,17 +980,17 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     pp.dbg = dbg_buf;
   }
-  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, om, pp);
+  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, om, g0 ? *g0 : om, g1 ? *g1 : om, pp);
   if (dbg_on) {
     long long h[256];
     NLAM_CUDA_OK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
     NLAM_CUDA_OK(cudaStreamSynchronize(st));
     long long t0 = h[0] ? h[0] : h[1];
     fprintf(stderr, "[nlam tc timeline] mode_edge=%d nb1=%d grid=%d work=%lld (cycles rel. to first event)\n", p.mode_edge, p.nb1, grid, n_work);
-    fprintf(stderr, " it    tma  g_start g_done   g1_iss  g2_iss | e_wait  d1_rdy  e1_done d2_rdy  ln_done staged  copied  reduced end\n");
+    fprintf(stderr, " it    tma  g_start g_done   g1_iss  g2_iss | e_wait  d1_rdy  e1_done d2_rdy  ln_done staged  copied  reduced end | g_issued g_pref\n");
     for (int it = 0; it < 8; ++it) {
       fprintf(stderr, "%3d ", it);
-      for (int k = 0; k < 14; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+      for (int k = 0; k < 16; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }
@@ -1014,7 +1098,7 @@ bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags) {
 
 int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
             int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-            cudaStream_t st) {
+            cudaStream_t st, int64_t send_rows) {
   NLAM_REQUIRE(tc_edge_supported(g, edge_mlp, flags), NLAM_E_UNSUPPORTED, "tc_edge: unsupported shape");
   NLAM_REQUIRE(aligned16(send) && aligned16(rec) && aligned16(edge) && aligned16(aggr_out) &&
                    (!edge_out || aligned16(edge_out)) && send_bs % 4 == 0 && rec_bs % 4 == 0 && edge_bs % 4 == 0,
@@ -1059,6 +1143,26 @@ int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int6
   if (edge_out) {
     rc = make_map(&om, edge_out, 64, (uint64_t)g->n_edges, (uint64_t)B, 64, (uint64_t)g->n_edges * 64, BM, true);
     if (rc) return rc;
+  }
+  // TMA gather4 maps over the sender / receiver node tensors: 2-D (64 x rows), box 32 x 1.  Usable when
+  // the batches are dense (stride = rows*64) or broadcast (stride 0); otherwise the cp.async path runs.
+  CUtensorMap g0, g1;
+  static int g4_env = -1;
+  if (g4_env < 0) g4_env = getenv("NLAM_TC_NO_GATHER4") ? 0 : 1;
+  const int64_t ns = g->n_send, nr = g->n_rec;
+  const bool dense0 = (send_bs == 0 || B == 1 || send_bs == send_rows * 64);
+  const bool dense1 = (rec_bs == 0 || B == 1 || rec_bs == nr * 64);
+  if (g4_env && dense0 && dense1 && send_rows >= ns) {
+    const uint64_t rows0 = (uint64_t)send_rows * ((send_bs == 0 || B == 1) ? 1 : B);
+    const uint64_t rows1 = (uint64_t)nr * ((rec_bs == 0 || B == 1) ? 1 : B);
+    rc = make_map(&g0, send, 64, rows0, 1, 64, 0, 1, false);
+    if (rc) return rc;
+    rc = make_map(&g1, rec, 64, rows1, 1, 64, 0, 1, false);
+    if (rc) return rc;
+    p.use_g4 = 1;
+    p.g4_rows[0] = (send_bs == 0 || B == 1) ? 0 : (int)send_rows;
+    p.g4_rows[1] = (rec_bs == 0 || B == 1) ? 0 : (int)nr;
+    return launch(a0, a1, w1, w2, om, p, st, &g0, &g1);
   }
   return launch(a0, a1, w1, w2, om, p, st);
 }
