@@ -348,17 +348,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   // misc region: mbarriers | tmem ptr | LayerNorm exchange | local CSR offsets
   const uint32_t mb = sbase + OFF_MISC;
   const uint32_t bar_w = mb + 0;
-  const uint32_t bar_a_gat_full = mb + 8;
-  const uint32_t bar_a_free_g = mb + 16;
-  const uint32_t bar_a_g4_full = mb + 24;  // gather4 mode: 1 arrival + 64 KB of TMA transactions
-  // stage-indexed (add 8*s)
-  const uint32_t bar_hb_full = mb + 96;
-  const uint32_t bar_a_tma_full = mb + 32;
-  const uint32_t bar_epi_done = mb + 48;
-  const uint32_t bar_d1_full = mb + 64;
-  const uint32_t bar_d2_full = mb + 80;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 120);
-  int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 128);  // local CSR offsets, <= 129 entries
+  const uint32_t bar_a_gat_full = mb + 8;   // produced blocks (cp.async / element-wise loaders): 128 arrivals
+  const uint32_t bar_a_free_g = mb + 16;    // ... and their release by the first GEMM's commit
+  // gather4 mode, per gathered source (+8*s): 1 arrival + 32 KB of TMA transactions / release by commit
+  const uint32_t bar_a_g4_full = mb + 24;
+  const uint32_t bar_a_g4_free = mb + 40;
+  // stage-indexed (+8*st)
+  const uint32_t bar_a_tma_full = mb + 56;
+  const uint32_t bar_epi_done = mb + 72;
+  const uint32_t bar_d1_full = mb + 88;
+  const uint32_t bar_d2_full = mb + 104;
+  const uint32_t bar_hb_full = mb + 120;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 136);
+  int* lp = reinterpret_cast<int*>(smem + OFF_MISC + 144);  // local CSR offsets, <= 129 entries
 
   if ((sbase & 1023u) != 0) {
     if (tid == 0) printf("nlam tc kernel: dynamic shared memory not 1024-byte aligned\n");
@@ -374,6 +376,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       mbar_init(bar_a_gat_full, PROD_THREADS);
       mbar_init(bar_a_free_g, 1);
       mbar_init(bar_a_g4_full, 1);
+      mbar_init(bar_a_g4_full + 8, 1);
+      mbar_init(bar_a_g4_free, 1);
+      mbar_init(bar_a_g4_free + 8, 1);
       for (int st = 0; st < 2; ++st) {
         mbar_init(bar_a_tma_full + 8 * st, 1);
         mbar_init(bar_epi_done + 8 * st, 1);
@@ -457,37 +462,76 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const uint64_t desc_a0 = umma_desc(sbase + OFF_A);
       const uint64_t desc_w1 = umma_desc(sbase + OFF_W1);
       const uint64_t desc_w2 = umma_desc(sbase + OFF_W2);
-      int g1 = 0, g2 = 0;
+      int g1 = 0, g2 = 0, g1_phase = 0;
       uint32_t idle = 0;
       while (g2 < n_my) {
         bool progress = false;
         if (g1 < n_my && g1 <= g2 + 1) {
+          // (g1 <= g2+1 also guarantees that epilogue 1 of tile g1-2 has drained this stage's D1.)
           const int it = g1, st = it & 1;
           const uint32_t sph = (uint32_t)((it >> 1) & 1);
-          bool ready = true;
-          if (has_tma_a) ready = mbar_test(bar_a_tma_full + 8 * st, sph);
-          else ready = mbar_test(bar_epi_done + 8 * st, sph ^ 1);  // accumulators of tile it-2 drained
-          if (ready && has_prod) ready = mbar_test(p.use_g4 ? bar_a_g4_full : bar_a_gat_full, (uint32_t)(it & 1));
-          if (ready) {
-            tc_fence_after();
-            NLAM_DBG(3, it);
-            const uint32_t d1 = tmem_base + st * 192;
-            for (int j = 0; j < p.nb1; ++j) {
-              // A block j: TMA blocks come from the stage, produced blocks (edge gathers) are fixed
-              int blk;
-              if (p.mode_edge) blk = (j < 2) ? (st ? 6 + j : j) : j;
-              else blk = has_tma_a ? (st ? stage_blk1 : 0) + j : j;
-              // descriptor = base + (byte offset >> 4) in the 14-bit start-address field (no carry:
-              // all operands live below 256 KB)
-              const uint64_t ad0 = desc_a0 + (uint64_t)((blk * A_BLOCK) >> 4);
-              const uint64_t bd0 = desc_w1 + (uint64_t)((j * W_BLOCK) >> 4);
+          const uint32_t d1 = tmem_base + st * 192;
+          if (p.mode_edge && p.use_g4) {
+            // operands arrive independently: sender rows, receiver rows, e tile.  Issue each K-slice as
+            // soon as it has landed and release its blocks right away, so that the next tile's gathers
+            // overlap the rest of this GEMM.
+            if (g1_phase < 2) {
+              if (mbar_test(bar_a_g4_full + 8 * g1_phase, (uint32_t)(it & 1))) {
+                tc_fence_after();
+                if (g1_phase == 0) NLAM_DBG(3, it);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(d1, ad0 + 2 * k, bd0 + 2 * k, idesc1, (uint32_t)((j | k) != 0));
+                for (int jj = 0; jj < 2; ++jj) {
+                  const int j = 2 + 2 * g1_phase + jj;
+                  const uint64_t ad0 = desc_a0 + (uint64_t)((j * A_BLOCK) >> 4);
+                  const uint64_t bd0 = desc_w1 + (uint64_t)((j * W_BLOCK) >> 4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_tf32(d1, ad0 + 2 * k, bd0 + 2 * k, idesc1, (uint32_t)((g1_phase | jj | k) != 0));
+                }
+                umma_commit(bar_a_g4_free + 8 * g1_phase);
+                ++g1_phase;
+                progress = true;
+              }
+            } else if (mbar_test(bar_a_tma_full + 8 * st, sph)) {
+              tc_fence_after();
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int blk = st ? 6 + j : j;
+                const uint64_t ad0 = desc_a0 + (uint64_t)((blk * A_BLOCK) >> 4);
+                const uint64_t bd0 = desc_w1 + (uint64_t)((j * W_BLOCK) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(d1, ad0 + 2 * k, bd0 + 2 * k, idesc1, 1u);
+              }
+              umma_commit(bar_d1_full + 8 * st);
+              g1_phase = 0;
+              ++g1;
+              progress = true;
             }
-            umma_commit(bar_d1_full + 8 * st);
-            if (has_prod) umma_commit(bar_a_free_g);
-            ++g1;
-            progress = true;
+          } else {
+            bool ready = true;
+            if (has_tma_a) ready = mbar_test(bar_a_tma_full + 8 * st, sph);
+            else ready = mbar_test(bar_epi_done + 8 * st, sph ^ 1);  // accumulators of tile it-2 drained
+            if (ready && has_prod) ready = mbar_test(bar_a_gat_full, (uint32_t)(it & 1));
+            if (ready) {
+              tc_fence_after();
+              NLAM_DBG(3, it);
+              for (int j = 0; j < p.nb1; ++j) {
+                // A block j: TMA blocks come from the stage, produced blocks (edge gathers) are fixed
+                int blk;
+                if (p.mode_edge) blk = (j < 2) ? (st ? 6 + j : j) : j;
+                else blk = has_tma_a ? (st ? stage_blk1 : 0) + j : j;
+                // descriptor = base + (byte offset >> 4) in the 14-bit start-address field (no carry:
+                // all operands live below 256 KB)
+                const uint64_t ad0 = desc_a0 + (uint64_t)((blk * A_BLOCK) >> 4);
+                const uint64_t bd0 = desc_w1 + (uint64_t)((j * W_BLOCK) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(d1, ad0 + 2 * k, bd0 + 2 * k, idesc1, (uint32_t)((j | k) != 0));
+              }
+              umma_commit(bar_d1_full + 8 * st);
+              if (has_prod) umma_commit(bar_a_free_g);
+              ++g1;
+              progress = true;
+            }
           }
         }
         if (g2 < g1) {
@@ -546,12 +590,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int b = w / p.n_tiles;
         const int t = w - b * p.n_tiles;
-        if (warp == W_PROD) {
-          mbar_wait(bar_a_free_g, (uint32_t)((it & 1) ^ 1));
-          // arm the transaction count before any producer thread can issue its gather
-          if (p.use_g4 && lane == 0) mbar_expect_tx(bar_a_g4_full, 4u * A_BLOCK);
+        if (p.use_g4) {
+          // producer threads 0-63 gather the sender rows, 64-127 the receiver rows; each half waits for
+          // ITS blocks to be released (the first GEMM commits after each source's MMAs) and arms its own
+          // transaction barrier before any of its threads can issue
+          const int half = pt >> 6;
+          if ((pt & 63) < 32) {  // leader warp of the half
+            mbar_wait(bar_a_g4_free + 8 * half, (uint32_t)((it & 1) ^ 1));
+            if (lane == 0) mbar_expect_tx(bar_a_g4_full + 8 * half, 2u * A_BLOCK);
+          }
+          named_bar_sync(8 + half, 64);
+        } else {
+          group_wait(warp == W_PROD, bar_a_free_g, (uint32_t)((it & 1) ^ 1), 8, PROD_THREADS);
         }
-        named_bar_sync(8, PROD_THREADS);
         if (pt == 0) NLAM_DBG(1, it);
         if (p.mode_edge && p.use_g4) {
           // TMA tile::gather4: producer thread pt issues ONE instruction = 4 gathered rows x 32 columns
@@ -562,8 +613,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           int r[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) r[u] = (4 * grp + u < pf_ne) ? pf4[u] + boff : 0;  // past the end: any valid row (never stored)
-          tma_gather4(sbase + OFF_A + (2 + 2 * sidx + jb) * A_BLOCK + grp * 512, sidx ? &tmG1 : &tmG0, bar_a_g4_full,
-                      32 * jb, r[0], r[1], r[2], r[3], pol_keep);
+          tma_gather4(sbase + OFF_A + (2 + 2 * sidx + jb) * A_BLOCK + grp * 512, sidx ? &tmG1 : &tmG0,
+                      bar_a_g4_full + 8 * sidx, 32 * jb, r[0], r[1], r[2], r[3], pol_keep);
           if (pt == 0) NLAM_DBG(14, it);
           {
             const int wn = w + (int)gridDim.x;
