@@ -24,7 +24,8 @@ extern "C" size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, in
   // message buffer (exact path) + aggregate buffer; 256-byte aligned sections
   size_t msg = ((size_t)B * g->n_edges * H * sizeof(float) + 255) / 256 * 256;
   size_t agg = ((size_t)B * g->n_rec * H * sizeof(float) + 255) / 256 * 256;
-  return msg + agg;
+  size_t proj = (H == 64) ? (tc_edge2_workspace_floats(g, B, 0) * sizeof(float) + 255) / 256 * 256 : 0;
+  return msg + agg + proj;
 }
 
 extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
@@ -59,7 +60,16 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   if (use_tc) {
     // rows of the sender tensor: known exactly when the batches are dense, else at least n_send
     const int64_t send_rows = (B > 1 && send_bs > 0) ? send_bs / H : g->n_send;
-    int rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
+    const size_t proj_bytes = tc_edge2_workspace_floats(g, B, 0) * sizeof(float);
+    int rc;
+    if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows) && workspace &&
+        ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
+      // split first Linear: node projections + K=64 edge kernel (tc2.cu)
+      rc = tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows,
+                    (float*)((char*)workspace + msg_bytes + agg_bytes));
+    } else {
+      rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
+    }
     if (rc) return rc;
   } else {
     NLAM_REQUIRE(workspace && ws_bytes >= msg_bytes, NLAM_E_WORKSPACE, "nlam_inet_fwd: workspace too small");

@@ -38,6 +38,13 @@ int64_t launch_count();
 
 constexpr int kTileEdges = 128;  // rows of one tensor-core edge tile (UMMA M)
 
+// tc2.cu: split-first-Linear edge kernel (v2) + node projection kernel
+bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
+                        const float* rec, int64_t rec_bs, int B, int64_t send_rows);
+size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_max);
+int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+             int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
+             cudaStream_t stream, int64_t send_rows, float* ws);
 }  // namespace nlam
 
 // Receiver-sorted CSR of one edge set + sender CSR + tensor-core tile table.
