@@ -12,13 +12,13 @@
 // Summation order differs from the reference (three TF32 GEMMs summed in fp32) — inside the stated
 // TF32 tolerance.
 //
-// tc_edge2_kernel: 704 threads, 1 CTA/SM, persistent over (batch, tile):
+// tc_edge2_kernel: 800 threads, 1 CTA/SM, persistent over (batch, tile):
 //   warps 0-7   epilogue-2 group 0 (tiles 0,2,4,..)   } D2 -> bias, LayerNorm, messages staged in the
 //   warps 8-15  epilogue-2 group 1 (tiles 1,3,5,..)   } tile's P_s buffer, e' = e + m in place + TMA
 //                                                       store, CSR segmented sum -> aggr
 //   warps 16-19 epilogue-1: D1 + P_s[src] (smem) + P_r[dst] (global) -> SiLU -> hidden in TMEM
 //   warp 20     tcgen05.mma issue (GEMM1 SS form K=64, GEMM2 TS form, A = hidden in TMEM)
-//   warp 21     TMA: weights once; per tile the e tile + 64 tile::gather4 (4 rows x 128 B each) of P_s
+//   warps 21-24 loaders: weights once; per tile the e tile (TMA) + 64 tile::gather4 (4 rows x 128 B) of P_s
 // Shared memory: W1e 16 KB | W2 16 KB | 3 stages x (e 32 KB + P_s 32 KB) | misc = 227 KB.
 // TMEM: 2 stages x (D 64 cols [D1, later D2] + hidden 64 cols) + LayerNorm scratch.
 #include "tc_ptx.cuh"
@@ -26,7 +26,9 @@
 namespace nlam {
 
 namespace e2 {
-constexpr int THREADS = 704;
+constexpr int THREADS = 800;
+constexpr int LD_THREADS = 128;  // 4 loader warps: a warp issues ~1 TMA operation per 100 cycles, so the
+                                 // 64 gather4 of a tile are spread over 4 warps x 16 lanes
 constexpr int G2_THREADS = 256;  // per epilogue-2 group
 constexpr int E1_THREADS = 128;
 constexpr int W_E1 = 16, W_MMA = 20, W_TMA = 21;
@@ -62,7 +64,13 @@ struct Edge2Params {
   const int32_t* tile_e0;
   const int4* tile_meta;
   const int32_t* rowptr;
+  long long* dbg;
 };
+
+#define E2_DBG(slot, it)                                                        \
+  do {                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(e2::THREADS, 1)
 tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmW1,
@@ -87,6 +95,10 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
   const uint32_t bar_d_free = mb + 104;   // [2] D2 drained into registers (256 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 120);
   int* lp_all = reinterpret_cast<int*>(smem + OFF_MISC + 128);  // [2 groups][132] local CSR offsets
+  float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 2048);  // b2 | gamma | beta (64 floats each):
+                                                                      // there is no L1 next to 227 KB of smem,
+                                                                      // so per-tile __ldg of constants costs an
+                                                                      // L2 round trip each
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -116,62 +128,72 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
     if (p.has_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  if (tid < 64) {
+    sprm[tid] = p.b2[tid];
+    sprm[64 + tid] = p.gamma[tid];
+    sprm[128 + tid] = p.beta[tid];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int n_work = p.n_tiles * p.B;
 
-  if (warp == W_TMA) {
-    // =============================== TMA ===============================
+  if (warp >= W_TMA) {
+    // =============================== loaders (4 warps) ===============================
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t pol_keep = policy_evict_last();
-    if (lane == 0) {
+    const int lw = warp - W_TMA;  // 0..3
+    if (lw == 0 && lane == 0) {
       mbar_expect_tx(bar_w, 4u * WBLK);
       for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W1 + j * WBLK, &tmW1, bar_w, 32 * j, 0);
       for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * WBLK, &tmW2, bar_w, 32 * j, 0);
     }
-    // sender ids of the first tile: lane l owns window rows 4l..4l+3
+    // lanes 0-15 of loader warp lw issue gather4 number op = lw*16 + lane: row group op&31 (window rows
+    // 4*grp..4*grp+3), column block op>>5.  Sender ids are prefetched one tile ahead.
+    const int op = lw * 16 + (lane & 15);
+    const int grp4 = op & 31, jb = op >> 5;
+    const bool issuer = lane < 16;
     int idx[4] = {0, 0, 0, 0};
-    int win = 0;
-    if ((int)blockIdx.x < n_work) {
+    if ((int)blockIdx.x < n_work && issuer) {
       const int e0 = p.tile_e0[(int)blockIdx.x % p.n_tiles];
-      win = (int)min((long long)BM, p.n_edges - e0);
+      const int win = (int)min((long long)BM, p.n_edges - e0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) idx[u] = (4 * lane + u < win) ? __ldg(p.src + e0 + 4 * lane + u) : 0;
+      for (int u = 0; u < 4; ++u) idx[u] = (4 * grp4 + u < win) ? __ldg(p.src + e0 + 4 * grp4 + u) : 0;
     }
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int b = w / p.n_tiles, t = w - b * p.n_tiles;
       const int s = it % NS;
       const uint32_t sph = (uint32_t)((it / NS) & 1);
-      const int e0 = p.tile_e0[t];
       const uint32_t full = bar_full + 8 * s;
       const uint32_t stg = sbase + OFF_ST + s * 4 * BLK;
-      if (lane == 0) {
-        mbar_wait(bar_epi_done + 8 * s, sph ^ 1);  // tile it-3 released the stage
-        mbar_expect_tx(full, 4u * BLK);
-        tma_load_3d(stg, &tmE, full, 0, e0, p.e_batched ? b : 0, pol_stream);
-        tma_load_3d(stg + BLK, &tmE, full, 32, e0, p.e_batched ? b : 0, pol_stream);
+      if (lw == 0) {
+        if (lane == 0) {
+          mbar_wait(bar_epi_done + 8 * s, sph ^ 1);  // tile it-3 released the stage
+          E2_DBG(0, it);
+          mbar_expect_tx(full, 4u * BLK);
+          const int e0 = p.tile_e0[t];
+          tma_load_3d(stg, &tmE, full, 0, e0, p.e_batched ? b : 0, pol_stream);
+          tma_load_3d(stg + BLK, &tmE, full, 32, e0, p.e_batched ? b : 0, pol_stream);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      {
+      named_bar_sync(12, LD_THREADS);  // stage free + transaction count armed
+      if (issuer) {
         const int boff = p.ps_rows * b;
         // rows past the end of the edge list gather row 0 (never stored)
-        tma_gather4(stg + 2 * BLK + lane * 512, &tmPs, full, 0, idx[0] + boff, idx[1] + boff, idx[2] + boff, idx[3] + boff,
-                    pol_keep);
-        tma_gather4(stg + 3 * BLK + lane * 512, &tmPs, full, 32, idx[0] + boff, idx[1] + boff, idx[2] + boff,
+        tma_gather4(stg + (2 + jb) * BLK + grp4 * 512, &tmPs, full, 32 * jb, idx[0] + boff, idx[1] + boff, idx[2] + boff,
                     idx[3] + boff, pol_keep);
-      }
-      // next tile: L2 prefetch of its e tile two iterations ahead, sender ids one iteration ahead
-      const int wn = w + (int)gridDim.x;
-      if (wn < n_work) {
-        const int e0n = p.tile_e0[wn % p.n_tiles];
-        win = (int)min((long long)BM, p.n_edges - e0n);
+        const int wn = w + (int)gridDim.x;
+        if (wn < n_work) {
+          const int e0n = p.tile_e0[wn % p.n_tiles];
+          const int win = (int)min((long long)BM, p.n_edges - e0n);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) idx[u] = (4 * lane + u < win) ? __ldg(p.src + e0n + 4 * lane + u) : 0;
+          for (int u = 0; u < 4; ++u) idx[u] = (4 * grp4 + u < win) ? __ldg(p.src + e0n + 4 * grp4 + u) : 0;
+        }
       }
-      if (lane == 0) {
+      if (lw == 0 && lane == 0) {
         const int w2 = w + 2 * (int)gridDim.x;
         if (w2 < n_work) {
           const int b2 = w2 / p.n_tiles, t2 = w2 - b2 * p.n_tiles;
@@ -201,6 +223,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
           if (mbar_test(bar_full + 8 * s, (uint32_t)((it / NS) & 1)) &&
               mbar_test(bar_d_free + 8 * ts, (uint32_t)(((it >> 1) & 1) ^ 1))) {
             tc_fence_after();
+            E2_DBG(3, it);
             const uint32_t d = tmem_base + ts * 128;
             const uint64_t a0 = desc_st + (uint64_t)((s * 4 * BLK) >> 4);
 #pragma unroll
@@ -218,6 +241,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
           const int it = g2, ts = it & 1;
           if (mbar_test(bar_hb_full + 8 * ts, (uint32_t)((it >> 1) & 1))) {
             tc_fence_after();
+            E2_DBG(4, it);
             const uint32_t d = tmem_base + ts * 128;  // D2 overwrites D1 (consumed by epilogue 1)
             const uint32_t ht = d + 64;
 #pragma unroll
@@ -272,6 +296,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       }
       named_bar_sync(1, E1_THREADS);
       tc_fence_after();
+      if (tid == W_E1 * 32) E2_DBG(6, it);
       const uint8_t* ps = smem + OFF_ST + s * 4 * BLK + 2 * BLK + rsw;
       const uint32_t d1 = tmem_base + ts * 128 + t_lane;
 #pragma unroll
@@ -300,6 +325,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
+      if (tid == W_E1 * 32) E2_DBG(7, it);
     }
   } else {
     // =============================== epilogue 2 (two groups, alternating tiles) ===============================
@@ -340,16 +366,18 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       if (gt <= nrec) lp[gt] = lp_val;  // previous tile of this group has passed its final barrier
       if (wn < n_work && gt <= meta_n.w) lp_val = __ldg(p.rowptr + meta_n.z + gt) - meta_n.x;
 
+      if (gt == 0) E2_DBG(5, it);
       if (gw == 0) mbar_wait(bar_d2_full + 8 * grp, tph);
       named_bar_sync(gbar, G2_THREADS);
       tc_fence_after();
+      if (gt == 0) E2_DBG(8, it);
       float v[32];
       tmem_ld32(tmem_base + grp * 128 + t_lane + c0, v);
       tc_fence_before();
       mbar_arrive(bar_d_free + 8 * grp);  // the TMEM stage may take the next tile's first GEMM
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 4 * k));
+        const float4 bb = *reinterpret_cast<const float4*>(sprm + c0 + 4 * k);
         v[4 * k + 0] += bb.x;
         v[4 * k + 1] += bb.y;
         v[4 * k + 2] += bb.z;
@@ -375,14 +403,15 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
         const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4 * k));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * k));
+          const float4 g4 = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k);
+          const float4 b4 = *reinterpret_cast<const float4*>(sprm + 128 + c0 + 4 * k);
           v[4 * k + 0] = (v[4 * k + 0] - mu) * rstd * g4.x + b4.x;
           v[4 * k + 1] = (v[4 * k + 1] - mu) * rstd * g4.y + b4.y;
           v[4 * k + 2] = (v[4 * k + 2] - mu) * rstd * g4.z + b4.z;
           v[4 * k + 3] = (v[4 * k + 3] - mu) * rstd * g4.w + b4.w;
         }
       }
+      if (gt == 0) E2_DBG(9, it);
       // messages -> the tile's P_s buffer (consumed by epilogue 1 long ago); e' = e + m in place
       uint8_t* stg = smem + OFF_ST + s * 4 * BLK;
       {
@@ -406,6 +435,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       }
       fence_proxy_async();
       named_bar_sync(gbar, G2_THREADS);
+      if (gt == 0) E2_DBG(10, it);
       if (p.has_out && gt == 0) {
         const uint32_t src = sbase + OFF_ST + s * 4 * BLK;
         tma_store_3d(&tmOut, src, 0, row0, b);
@@ -431,8 +461,10 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
           *reinterpret_cast<float4*>(p.aggr + ((long long)b * p.n_rec + r0 + j) * 64 + cg * 4) = acc;
         }
       }
+      if (gt == 0) E2_DBG(12, it);
       if (gt == 0 && p.has_out) bulk_wait_read0();
       named_bar_sync(gbar, G2_THREADS);
+      if (gt == 0) E2_DBG(13, it);
       if (gt == 0) mbar_arrive(bar_epi_done + 8 * s);
       meta = meta_n;
       meta_n = meta_nn;
@@ -709,8 +741,29 @@ int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
   const long long n_work = (long long)p.n_tiles * p.B;
   NLAM_REQUIRE(n_work < (1LL << 31) - 4096, NLAM_E_UNSUPPORTED, "tc_edge2: too many work items");
   const int grid = (int)std::min<long long>(n_work, num_sms());
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("NLAM_TC_TIMELINE") ? 1 : 0;
+  if (dbg_on) {
+    if (!dbg_buf) NLAM_CUDA_OK(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+    NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
+    p.dbg = dbg_buf;
+  }
   tc_edge2_kernel<<<grid, e2::THREADS, e2::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
   count_launch();
+  if (dbg_on) {
+    long long h[256];
+    NLAM_CUDA_OK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+    NLAM_CUDA_OK(cudaStreamSynchronize(st));
+    long long t0 = h[0];
+    fprintf(stderr, "[nlam tc_edge2 timeline] grid=%d work=%lld (cycles rel. to first TMA issue)\n", grid, n_work);
+    fprintf(stderr, " it    tma       -       -  g1_iss  g2_iss  e2wait  d1_rdy e1_done  d2_rdy  ln_done  staged       - reduced     end\n");
+    for (int it = 0; it < 12; ++it) {
+      fprintf(stderr, "%3d ", it);
+      for (int k = 0; k < 14; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
