@@ -12,13 +12,14 @@
 // Summation order differs from the reference (three TF32 GEMMs summed in fp32) — inside the stated
 // TF32 tolerance.
 //
-// tc_edge2_kernel: 800 threads, 1 CTA/SM, persistent over (batch, tile):
+// tc_edge2_kernel: 896 threads, 1 CTA/SM, persistent over (batch, tile):
 //   warps 0-7   epilogue-2 group 0 (tiles 0,2,4,..)   } D2 -> bias, LayerNorm, messages staged in the
 //   warps 8-15  epilogue-2 group 1 (tiles 1,3,5,..)   } tile's P_s buffer, e' = e + m in place + TMA
 //                                                       store, CSR segmented sum -> aggr
-//   warps 16-19 epilogue-1: D1 + P_s[src] (smem) + P_r[dst] (global) -> SiLU -> hidden in TMEM
-//   warp 20     tcgen05.mma issue (GEMM1 SS form K=64, GEMM2 TS form, A = hidden in TMEM)
-//   warps 21-24 loaders: weights once; per tile the e tile (TMA) + 64 tile::gather4 (4 rows x 128 B) of P_s
+//   warps 16-23 epilogue-1, two groups alternating tiles: D1 + P_s[src] (smem) + P_r[dst] (global) ->
+//               SiLU -> hidden in TMEM
+//   warp 24     tcgen05.mma issue (GEMM1 SS form K=64, GEMM2 TS form, A = hidden in TMEM)
+//   warps 25-27 loaders: weights once; per tile the e tile (TMA) + 64 tile::gather4 (4 rows x 128 B) of P_s
 // Shared memory: W1e 16 KB | W2 16 KB | 3 stages x (e 32 KB + P_s 32 KB) | misc = 227 KB.
 // TMEM: 2 stages x (D 64 cols [D1, later D2] + hidden 64 cols) + LayerNorm scratch.
 #include "tc_ptx.cuh"
@@ -26,12 +27,12 @@
 namespace nlam {
 
 namespace e2 {
-constexpr int THREADS = 800;
-constexpr int LD_THREADS = 128;  // 4 loader warps: a warp issues ~1 TMA operation per 100 cycles, so the
+constexpr int THREADS = 896;
+constexpr int LD_THREADS = 96;   // 4 loader warps: a warp issues ~1 TMA operation per 100 cycles, so the
                                  // 64 gather4 of a tile are spread over 4 warps x 16 lanes
 constexpr int G2_THREADS = 256;  // per epilogue-2 group
 constexpr int E1_THREADS = 128;
-constexpr int W_E1 = 16, W_MMA = 20, W_TMA = 21;
+constexpr int W_E1 = 16, W_MMA = 24, W_TMA = 25;  // E1: two groups of 4 warps (16-19, 20-23); loaders 25-27
 constexpr int BM = 128;
 constexpr int NS = 3;  // shared-memory stages
 constexpr uint32_t BLK = 16384;
@@ -151,9 +152,9 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     }
     // lanes 0-15 of loader warp lw issue gather4 number op = lw*16 + lane: row group op&31 (window rows
     // 4*grp..4*grp+3), column block op>>5.  Sender ids are prefetched one tile ahead.
-    const int op = lw * 16 + (lane & 15);
-    const int grp4 = op & 31, jb = op >> 5;
-    const bool issuer = lane < 16;
+    const int op = lw * 22 + lane;
+    const int grp4 = op & 31, jb = (op >> 5) & 1;
+    const bool issuer = lane < 22 && op < 64;
     int idx[4] = {0, 0, 0, 0};
     if ((int)blockIdx.x < n_work && issuer) {
       const int e0 = p.tile_e0[(int)blockIdx.x % p.n_tiles];
@@ -264,22 +265,28 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     }
   } else if (warp >= W_E1) {
     // =============================== epilogue 1 ===============================
+    // two groups of 4 warps alternate tiles (group = TMEM stage), like the second epilogue
+    const int g1g = (warp - W_E1) >> 2;
+    const bool g1lead = ((warp - W_E1) & 3) == 0;
+    const int g1bar = g1g ? 13 : 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
     const uint32_t rsw = (uint32_t)(row * 128);
     const int rx = row & 7;
+    const int stride1 = 2 * (int)gridDim.x;
+    const int w_first1 = (int)blockIdx.x + g1g * (int)gridDim.x;
     int dst_next = 0;
-    if ((int)blockIdx.x < n_work) {
-      const int e0 = p.tile_e0[(int)blockIdx.x % p.n_tiles];
+    if (w_first1 < n_work) {
+      const int e0 = p.tile_e0[w_first1 % p.n_tiles];
       dst_next = (e0 + row < p.n_edges) ? __ldg(p.dst + e0 + row) : 0;
     }
-    int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    int it = g1g;
+    for (int w = w_first1; w < n_work; w += stride1, it += 2) {
       const int b = w / p.n_tiles;
       const int ts = it & 1, s = it % NS;
       const int my_dst = dst_next;
-      const int wn = w + (int)gridDim.x;
+      const int wn = w + stride1;
       if (wn < n_work) {
         const int e0n = p.tile_e0[wn % p.n_tiles];
         dst_next = (e0n + row < p.n_edges) ? __ldg(p.dst + e0n + row) : 0;
@@ -290,13 +297,13 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       float4 pr_cur[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) pr_cur[k] = __ldg(prow + k);
-      if (warp == W_E1) {
+      if (g1lead) {
         mbar_wait(bar_full + 8 * s, (uint32_t)((it / NS) & 1));  // P_s rows of this tile visible
         mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((it >> 1) & 1));
       }
-      named_bar_sync(1, E1_THREADS);
+      named_bar_sync(g1bar, E1_THREADS);
       tc_fence_after();
-      if (tid == W_E1 * 32) E2_DBG(6, it);
+      if (g1lead && lane == 0) E2_DBG(6, it);
       const uint8_t* ps = smem + OFF_ST + s * 4 * BLK + 2 * BLK + rsw;
       const uint32_t d1 = tmem_base + ts * 128 + t_lane;
 #pragma unroll
@@ -325,7 +332,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
-      if (tid == W_E1 * 32) E2_DBG(7, it);
+      if (g1lead && lane == 0) E2_DBG(7, it);
     }
   } else {
     // =============================== epilogue 2 (two groups, alternating tiles) ===============================
