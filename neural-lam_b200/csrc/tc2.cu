@@ -665,13 +665,22 @@ static int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, co
 
 bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                         const float* rec, int64_t rec_bs, int B, int64_t send_rows) {
-  (void)B;
   (void)send_rows;
-  static int on = -1;
-  if (on < 0) on = getenv("NLAM_TC_EDGE_V1") ? 0 : 1;
-  if (!on) return false;
+  // NLAM_TC_EDGE=v1 | v2 forces one formulation; default: the split kernel where its per-node projection
+  // passes are small next to the edge work (large edge sets such as mesh->grid), the K=192 kernel otherwise
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("NLAM_TC_EDGE");
+    mode = (e && e[0] == 'v' && e[1] == '1') ? 1 : (e && e[0] == 'v' && e[1] == '2') ? 2 : 0;
+  }
+  if (mode == 1) return false;
   if (!tc_edge_supported(g, edge_mlp, flags)) return false;
-  return aligned16(send) && aligned16(rec) && send_bs % 4 == 0 && rec_bs % 4 == 0;
+  if (!(aligned16(send) && aligned16(rec) && send_bs % 4 == 0 && rec_bs % 4 == 0)) return false;
+  if (mode == 2) return true;
+  const double edge_rows = (double)g->n_edges * B;
+  const double node_rows = (double)g->n_send * ((send_bs == 0 || B == 1) ? 1 : B) +
+                           (double)g->n_rec * ((rec_bs == 0 || B == 1) ? 1 : B);
+  return edge_rows >= 1.0e6 && edge_rows >= 3.0 * node_rows;
 }
 
 size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_max) {

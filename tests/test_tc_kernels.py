@@ -187,3 +187,48 @@ def test_model_rollout_tf32_vs_oracle(kind):
     err = (got.double().cpu() - want).abs().max().item()
     assert err <= 5e-2 and err <= max(3 * ref_err, 1e-2), (err, ref_err)
     torch.testing.assert_close(got_g, got, rtol=1e-6, atol=1e-6)
+
+
+def test_split_edge_kernel_v2_matches_v1_and_oracle():
+    """The split-first-Linear edge kernel (tc2.cu; forced with NLAM_TC_EDGE=v2 in a fresh process,
+    the selection is read once per process) against the fp64 oracle and the K=192 kernel."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import neural_lam_b200 as nlb
+from oracle import reference_port as rp
+g = torch.Generator().manual_seed(1)
+ns, nr, ne, B = 300, 300, 2600, 3
+ei = torch.stack([torch.randint(0, ns, (ne,), generator=g), torch.randint(0, nr, (ne,), generator=g)])
+ei[1, -1] = nr - 1
+ei = ei[:, torch.sort(ei[1], stable=True).indices]
+torch.manual_seed(0)
+res = {}
+for upd, aggr in ((True, "sum"), (False, "mean")):
+    net = nlb.InteractionNet(ei, 64, update_edges=upd, aggr=aggr, math="tf32")
+    send, edge = torch.randn(B, ns, 64), torch.randn(B, ne, 64)
+    want = rp.interaction_net({k: v.double() for k, v in net.state_dict().items()}, ei, send.double(), send.double(),
+                              edge.double(), aggr=aggr, update_edges=upd)
+    net = net.cuda()
+    with torch.no_grad():
+        got = net(send.cuda(), send.cuda(), edge.cuda())
+    got = got if isinstance(got, tuple) else (got,)
+    want = want if isinstance(want, tuple) else (want,)
+    err = max((a.double().cpu() - b).abs().max().item() for a, b in zip(got, want))
+    print("ERR", err)
+    assert err < 1e-2, err
+print("LAUNCHES", nlb._lib.lib().nlam_launch_count())
+'''
+    outs = {}
+    for mode in ("v1", "v2"):
+        env = dict(os.environ, NLAM_TC_EDGE=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[mode] = int([l for l in r.stdout.splitlines() if l.startswith("LAUNCHES")][0].split()[1])
+    # v2 issues two extra node-projection launches per InteractionNet call
+    assert outs["v2"] == outs["v1"] + 2 * 2
