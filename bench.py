@@ -6,7 +6,9 @@ mesh (6 561 nodes, 57 616 m2m / 100 656 g2m / 255 136 m2g edges), GraphLAM hidde
 4 processor layers, fp32 I/O, synthetic inputs (seeded), random-init weights (seed 42).
 
 One "step" = one autoregressive forecast step (StepPredictor.forward + boundary mix) for a
-batch of B independent forecasts on each GPU; value = forecast-steps/sec = N*B*K / t.
+batch of B independent forecasts (default 32: every sample shares graph and weights, so the batch is
+a pure extra row dimension; it also pushes the working set far past the 126 MB L2) on each GPU;
+value = forecast-steps/sec = N*B*K / t.
   * `value`     : inputs resident in HBM, the step replayed from a CUDA graph.
   * `e2e`       : ARForecaster public call path with HOST (pinned) buffers: every step copies that
                   step's forcing + boundary states host->device and the predicted state
@@ -370,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="forecasts per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="independent forecasts (ensemble members) per GPU per step")
     ap.add_argument("--math", default="auto", choices=["auto", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
