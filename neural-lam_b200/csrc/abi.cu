@@ -62,7 +62,12 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
     const int64_t send_rows = (B > 1 && send_bs > 0) ? send_bs / H : g->n_send;
     const size_t proj_bytes = tc_edge2_workspace_floats(g, B, 0) * sizeof(float);
     int rc;
-    if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows) && workspace &&
+    if (tc_ell_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge_out != nullptr) && workspace &&
+        ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
+      // uniform in-degree: receiver-tiled ELL kernel, aggregation in registers (tc3.cu)
+      rc = tc_ell_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, aggr, B, flags, st,
+                       (float*)((char*)workspace + msg_bytes + agg_bytes));
+    } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows) && workspace &&
         ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
       // split first Linear: node projections + K=64 edge kernel (tc2.cu)
       rc = tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows,

@@ -45,6 +45,12 @@ size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_ma
 int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, int64_t send_rows, float* ws);
+// tc3.cu
+bool tc_ell_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
+                      const float* rec, int64_t rec_bs, bool has_edge_out);
+int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                int64_t rec_bs, const float* edge, int64_t edge_bs, float* aggr_out, int B, int flags,
+                cudaStream_t stream, float* ws);
 }  // namespace nlam
 
 // Receiver-sorted CSR of one edge set + sender CSR + tensor-core tile table.
@@ -53,6 +59,7 @@ struct NlamGraph {
   int64_t n_edges = 0, n_rec = 0, n_send = 0;
   int32_t max_in_degree = 0;
   int32_t is_sorted = 0;
+  int32_t uniform_degree = 0;   // d if every receiver has exactly d incoming edges (E = d * n_rec), else 0
   // device arrays (int32)
   int32_t* rowptr = nullptr;    // n_rec+1
   int32_t* src = nullptr;       // E, sender of CSR edge k

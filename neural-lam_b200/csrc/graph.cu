@@ -83,6 +83,11 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
   }
   g->max_in_degree = maxdeg;
   g->is_sorted = sorted ? 1 : 0;
+  {
+    bool uniform = maxdeg >= 1 && (int64_t)maxdeg * n_rec == E;
+    for (int64_t r = 0; uniform && r < n_rec; ++r) uniform = (rowptr[r + 1] - rowptr[r]) == maxdeg;
+    g->uniform_degree = uniform ? maxdeg : 0;
+  }
 
   // sender CSR over CSR-ordered edges (stable): backward of the sender gather
   std::vector<int32_t> sptr(n_send + 1, 0), sperm(E);

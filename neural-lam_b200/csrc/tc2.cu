@@ -630,7 +630,7 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ host
-static int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const float* wslice, int ldw,
+int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const float* wslice, int ldw,
                      const float* bias, float* out, cudaStream_t st) {
   CUtensorMap mx, mw, mo;
   const bool batched = B_eff > 1;
