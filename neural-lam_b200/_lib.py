@@ -65,6 +65,8 @@ SYMBOLS = {
     "nlam_graph_num_send": (ctypes.c_int64, [ctypes.c_void_p]),
     "nlam_graph_max_in_degree": (ctypes.c_int32, [ctypes.c_void_p]),
     "nlam_graph_is_sorted": (ctypes.c_int32, [ctypes.c_void_p]),
+    "nlam_graph_uniform_degree": (ctypes.c_int32, [ctypes.c_void_p]),
+    "nlam_graph_ell_window": (ctypes.c_int32, [ctypes.c_void_p]),
     "nlam_graph_rowptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nlam_graph_src": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nlam_graph_dst": (ctypes.c_void_p, [ctypes.c_void_p]),

@@ -75,6 +75,13 @@ struct NlamGraph {
   int32_t* tile_rec = nullptr;  // n_tiles+1
   int32_t* tile_e0 = nullptr;   // n_tiles+1: first CSR edge of each tile
   int32_t* tile_meta = nullptr; // 4*n_tiles: {first edge, #edges, first receiver, #receivers}
+  // uniform in-degree (ELL) sender windows: receiver tile t (128 receivers) reads ell_nu[t] <= 128 distinct
+  // senders ell_u[128*t ..] (ascending, padded to a multiple of 4); CSR edge k reads window row ell_loc[k].
+  // ell_window == 0 if some tile reads more than 128 distinct senders (or the degree is not uniform).
+  int32_t ell_window = 0;
+  int32_t* ell_u = nullptr;
+  int32_t* ell_nu = nullptr;
+  uint8_t* ell_loc = nullptr;
   std::vector<int32_t> h_tile_rec, h_rowptr;
 };
 

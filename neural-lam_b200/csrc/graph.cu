@@ -120,6 +120,38 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
     tile_meta.push_back(tile_rec[i]);
     tile_meta.push_back(tile_rec[i + 1] - tile_rec[i]);
   }
+  // sender windows of the ELL kernel (tc3.cu)
+  std::vector<int32_t> ell_u, ell_nu;
+  std::vector<uint8_t> ell_loc;
+  if (g->uniform_degree >= 1 && g->uniform_degree <= 8) {
+    const int64_t d = g->uniform_degree, nt = (n_rec + 127) / 128;
+    ell_u.assign((size_t)nt * 128, 0);
+    ell_nu.assign((size_t)nt, 0);
+    ell_loc.assign((size_t)E, 0);
+    bool ok = true;
+    std::vector<int32_t> u;
+    for (int64_t t = 0; t < nt && ok; ++t) {
+      const int64_t k0 = d * 128 * t, k1 = std::min<int64_t>(E, d * 128 * (t + 1));
+      u.assign(src.begin() + k0, src.begin() + k1);
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      if (u.size() > 128) {
+        ok = false;
+        break;
+      }
+      for (int64_t k = k0; k < k1; ++k)
+        ell_loc[k] = (uint8_t)(std::lower_bound(u.begin(), u.end(), src[k]) - u.begin());
+      const size_t nu = (u.size() + 3) / 4 * 4;
+      for (size_t i = 0; i < nu; ++i) ell_u[(size_t)t * 128 + i] = u[std::min(i, u.size() - 1)];
+      ell_nu[t] = (int32_t)nu;
+    }
+    g->ell_window = ok ? 1 : 0;
+    if (!ok) {
+      ell_u.clear();
+      ell_nu.clear();
+      ell_loc.clear();
+    }
+  }
   g->h_tile_rec = tile_rec;
   g->h_rowptr = rowptr;
 
@@ -141,7 +173,8 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
       (rc = upload(&g->perm, perm)) || (rc = upload(&g->inv_perm, inv_perm)) ||
       (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
       (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0)) ||
-      (rc = upload(&g->tile_meta, tile_meta))) {
+      (rc = upload(&g->tile_meta, tile_meta)) || (rc = upload(&g->ell_u, ell_u)) ||
+      (rc = upload(&g->ell_nu, ell_nu)) || (rc = upload(&g->ell_loc, ell_loc))) {
     cudaSetDevice(prev_dev);
     nlam_graph_destroy(g);
     return rc;
@@ -166,6 +199,9 @@ extern "C" void nlam_graph_destroy(NlamGraph* g) {
   cudaFree(g->tile_rec);
   cudaFree(g->tile_e0);
   cudaFree(g->tile_meta);
+  cudaFree(g->ell_u);
+  cudaFree(g->ell_nu);
+  cudaFree(g->ell_loc);
   cudaSetDevice(prev);
   delete g;
 }
@@ -175,6 +211,8 @@ extern "C" int64_t nlam_graph_num_rec(const NlamGraph* g) { return g->n_rec; }
 extern "C" int64_t nlam_graph_num_send(const NlamGraph* g) { return g->n_send; }
 extern "C" int32_t nlam_graph_max_in_degree(const NlamGraph* g) { return g->max_in_degree; }
 extern "C" int32_t nlam_graph_is_sorted(const NlamGraph* g) { return g->is_sorted; }
+extern "C" int32_t nlam_graph_uniform_degree(const NlamGraph* g) { return g->uniform_degree; }
+extern "C" int32_t nlam_graph_ell_window(const NlamGraph* g) { return g->ell_window; }
 extern "C" const int32_t* nlam_graph_rowptr(const NlamGraph* g) { return g->rowptr; }
 extern "C" const int32_t* nlam_graph_src(const NlamGraph* g) { return g->src; }
 extern "C" const int32_t* nlam_graph_dst(const NlamGraph* g) { return g->dst; }

@@ -13,7 +13,7 @@
 //     no per-edge receiver gather and no receiver projection pass over the grid;
 //   * a shared-memory stage (e slice + gathered P_s rows) is released right after epilogue 1, so two
 //     stages keep the pipeline full.
-// z1 = e·W1eᵀ + (x_s·W1sᵀ)[src] + x_r·W1rᵀ + b1 ; h = SiLU(z1) ; m = LN(h·W2ᵀ + b2) ; aggr = sum|mean_k m_k.
+// z1 = e·W1eᵀ + (x_s·W1sᵀ + b1)[src] + x_r·W1rᵀ ; h = SiLU(z1) ; m = LN(h·W2ᵀ + b2) ; aggr = sum|mean_k m_k.
 // P_s = x_s·W1sᵀ comes from tc_rowlinear_kernel (tc2.cu) over the (small) sender set.
 //
 // 640 threads: warps 0-7 epilogue 2 (thread = receiver row x 32 columns, accumulator in registers),
@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(e3::THREADS, 1)
@@ -308,11 +314,10 @@ tc_ell_edge_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const float4 s4 = *reinterpret_cast<const float4*>(psb + ((((c & 1) * 4 + k4) ^ rx) << 4));
-          const float4 b4 = *reinterpret_cast<const float4*>(sprm + c * 16 + 4 * k4);
-          v[4 * k4 + 0] = silu_fast(v[4 * k4 + 0] + r[4 * k4 + 0] + s4.x + b4.x);
-          v[4 * k4 + 1] = silu_fast(v[4 * k4 + 1] + r[4 * k4 + 1] + s4.y + b4.y);
-          v[4 * k4 + 2] = silu_fast(v[4 * k4 + 2] + r[4 * k4 + 2] + s4.z + b4.z);
-          v[4 * k4 + 3] = silu_fast(v[4 * k4 + 3] + r[4 * k4 + 3] + s4.w + b4.w);
+          v[4 * k4 + 0] = silu_fast(v[4 * k4 + 0] + r[4 * k4 + 0] + s4.x);  // P_s carries b1
+          v[4 * k4 + 1] = silu_fast(v[4 * k4 + 1] + r[4 * k4 + 1] + s4.y);
+          v[4 * k4 + 2] = silu_fast(v[4 * k4 + 2] + r[4 * k4 + 2] + s4.z);
+          v[4 * k4 + 3] = silu_fast(v[4 * k4 + 3] + r[4 * k4 + 3] + s4.w);
         }
         tmem_st16(d1 + 64 + c * 16, v);
       }
@@ -405,6 +410,479 @@ tc_ell_edge_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sender-window variant: the 128*d edges of a receiver tile usually read far fewer than 128*d DISTINCT
+// senders (mesh->grid on MEPS: ~90 mesh nodes serve the 512 edges of a tile).  The graph handle lists
+// the distinct senders of every tile (<= 128, else this variant is not used) and the window row of every
+// edge, so P_s is gathered ONCE per tile (<= 64 gather4 operations instead of 64 per sub-tile) and
+// epilogue 1 reads its row of the window by index.  Shared memory then holds two windows (tile double
+// buffer) and a 3-slot ring of 32 KB operand tiles (receiver tile, then the d edge slices of the tile);
+// a ring slot is released by the commit of the GEMM that read it.
+namespace e4 {
+constexpr int THREADS = 640;
+constexpr int G2_THREADS = 256;
+constexpr int E1_THREADS = 256;
+constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_GA = 18;
+constexpr int NR = 3;
+constexpr uint32_t BLK = 16384;
+constexpr uint32_t WBLK = 8192;
+constexpr uint32_t OFF_W1E = 0;
+constexpr uint32_t OFF_W1R = 2 * WBLK;
+constexpr uint32_t OFF_W2 = 4 * WBLK;
+constexpr uint32_t OFF_WIN = 6 * WBLK;              // 2 sender windows x 32 KB
+constexpr uint32_t OFF_RING = OFF_WIN + 4 * BLK;    // NR operand tiles x 32 KB
+constexpr uint32_t OFF_MISC = OFF_RING + NR * 2 * BLK;
+constexpr uint32_t SMEM = OFF_MISC + 2048;
+}  // namespace e4
+
+struct EllWinParams {
+  const int32_t* win_u;   // 128 sender ids per tile
+  const int32_t* win_nu;  // window rows per tile (multiple of 4)
+  const uint8_t* loc;     // window row of every CSR edge
+  int d;
+  int ps_rows;
+  const float* b1;
+  const float* b2;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* aggr;
+  int e_batched, rec_batched;
+  int mean;
+  long long n_rec;
+  int B;
+  int n_tiles;
+  int prefetch;
+  long long* dbg;
+};
+
+__global__ void __launch_bounds__(e4::THREADS, 1)
+tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmRec,
+                     const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                     const __grid_constant__ CUtensorMap tmPs, const __grid_constant__ CUtensorMap tmOut,
+                     const EllWinParams p) {
+  using namespace e4;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((sbase & 1023u) != 0) {
+    if (tid == 0) printf("nlam tc_ell_window: dynamic shared memory not 1024-byte aligned\n");
+    __trap();
+  }
+  const uint32_t mb = sbase + OFF_MISC;
+  const uint32_t bar_w = mb + 0;
+  const uint32_t bar_ring_full = mb + 8;    // [3]
+  const uint32_t bar_ring_free = mb + 32;   // [3] commit of the GEMM that read the slot
+  const uint32_t bar_win_full = mb + 56;    // [2] sender window gathered
+  const uint32_t bar_staged = mb + 72;      // [2] aggregate of the tile staged in its window buffer (256 arrivals)
+  const uint32_t bar_dr_full = mb + 88;     // [2]
+  const uint32_t bar_d1_full = mb + 104;    // [2]
+  const uint32_t bar_hb_full = mb + 120;    // [2]
+  const uint32_t bar_d2_full = mb + 136;    // [2]
+  const uint32_t bar_d_free = mb + 152;     // [2]
+  const uint32_t bar_wscaled = mb + 168;    // first-Linear weight tiles halved in place (256 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 176);
+  float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 256);  // b1 | b2 | gamma | beta
+  const int d = p.d;
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1);
+      mbar_init(bar_wscaled, E1_THREADS);
+      for (int t = 0; t < NR; ++t) {
+        mbar_init(bar_ring_full + 8 * t, 1);
+        mbar_init(bar_ring_free + 8 * t, 1);
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(bar_win_full + 8 * t, 1);
+        mbar_init(bar_staged + 8 * t, G2_THREADS);
+        mbar_init(bar_dr_full + 8 * t, 1);
+        mbar_init(bar_d1_full + 8 * t, 1);
+        mbar_init(bar_hb_full + 8 * t, E1_THREADS);
+        mbar_init(bar_d2_full + 8 * t, 1);
+        mbar_init(bar_d_free + 8 * t, G2_THREADS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == W_RING && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRec) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+  }
+  if (tid < 64) {
+    sprm[tid] = p.b1[tid];
+    sprm[64 + tid] = p.b2[tid];
+    sprm[128 + tid] = p.gamma[tid];
+    sprm[192 + tid] = p.beta[tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // TMEM columns: D_r[tile parity] at 0 / 64; sub-tile stage ts: D at 128 + ts*128, hidden +64; LN scratch 384
+  const int n_work = p.n_tiles * p.B;
+  int n_my = 0;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
+  const int n_sub = n_my * d;
+
+  if (warp == W_RING) {
+    // =============================== operand ring: receiver tile, then d edge slices, per tile ===============
+    if (lane == 0) {
+      const uint64_t pol_stream = policy_evict_first();
+      const uint64_t pol_e = p.e_batched ? pol_stream : policy_evict_last();  // broadcast edge rows are re-read per batch
+      mbar_expect_tx(bar_w, 6u * WBLK);
+      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W1E + j * WBLK, &tmW1, bar_w, 32 * j, 0);
+      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W1R + j * WBLK, &tmW1, bar_w, 128 + 32 * j, 0);
+      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * WBLK, &tmW2, bar_w, 32 * j, 0);
+      int i = 0;
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int r0 = t * 128;
+        if (p.prefetch && ti + 1 < n_my) {
+          // pull the next tile's operands into L2 while this one is processed
+          const int wn = w + gridDim.x;
+          const int bn = wn / p.n_tiles, tn = wn - bn * p.n_tiles;
+          tma_prefetch_3d(&tmRec, 0, tn * 128, p.rec_batched ? bn : 0);
+          tma_prefetch_3d(&tmRec, 32, tn * 128, p.rec_batched ? bn : 0);
+          for (int k = 0; k < d; ++k) {
+            tma_prefetch_4d(&tmE, 0, k, tn * 128, p.e_batched ? bn : 0);
+            tma_prefetch_4d(&tmE, 32, k, tn * 128, p.e_batched ? bn : 0);
+          }
+        }
+        for (int m = 0; m <= d; ++m, ++i) {
+          const int slot = i % NR;
+          const uint32_t dst = sbase + OFF_RING + slot * 2 * BLK;
+          const uint32_t full = bar_ring_full + 8 * slot;
+          mbar_wait(bar_ring_free + 8 * slot, (uint32_t)(((i / NR) & 1) ^ 1));
+          mbar_expect_tx(full, 2u * BLK);
+          if (m == 0) {
+            E3_DBG(0, ti * d);
+            tma_load_3d(dst, &tmRec, full, 0, r0, p.rec_batched ? b : 0, pol_stream);
+            tma_load_3d(dst + BLK, &tmRec, full, 32, r0, p.rec_batched ? b : 0, pol_stream);
+          } else {
+            tma_load_4d(dst, &tmE, full, 0, m - 1, r0, p.e_batched ? b : 0, pol_e);
+            tma_load_4d(dst + BLK, &tmE, full, 32, m - 1, r0, p.e_batched ? b : 0, pol_e);
+          }
+        }
+      }
+    }
+  } else if (warp >= W_GA) {
+    // =============================== sender windows: one gather per tile (2 warps, 64 gather4 operations) ========
+    const uint64_t pol_keep = policy_evict_last();
+    const int gt = (warp - W_GA) * 32 + lane;
+    const int grp4 = gt & 31, jb = gt >> 5;
+    for (int ti = 0; ti < n_my; ++ti) {
+      const int w = blockIdx.x + ti * gridDim.x;
+      const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+      const int ngrp = __ldg(p.win_nu + t) >> 2;
+      int4 ids = make_int4(0, 0, 0, 0);
+      if (grp4 < ngrp) ids = __ldg(reinterpret_cast<const int4*>(p.win_u + (size_t)t * 128) + grp4);
+      const uint32_t full = bar_win_full + 8 * (ti & 1);
+      if (gt == 0) {
+        if (ti >= 2) {
+          // the buffer holds the staged aggregate of tile ti-2: store it, then reuse the buffer
+          const int wp = w - 2 * gridDim.x;
+          const int bp = wp / p.n_tiles, tp = wp - bp * p.n_tiles;
+          mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)(((ti - 2) >> 1) & 1));
+          const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
+          tma_store_3d(&tmOut, src, 0, tp * 128, bp);
+          tma_store_3d(&tmOut, src + BLK, 32, tp * 128, bp);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+        mbar_expect_tx(full, (uint32_t)ngrp * 1024u);
+      }
+      named_bar_sync(12, 64);
+      if (grp4 < ngrp) {
+        const int boff = p.ps_rows * b;
+        tma_gather4(sbase + OFF_WIN + (ti & 1) * 2 * BLK + jb * BLK + grp4 * 512, &tmPs, full, 32 * jb, ids.x + boff,
+                    ids.y + boff, ids.z + boff, ids.w + boff, pol_keep);
+      }
+    }
+    if (gt == 0) {
+      for (int ti = (n_my >= 2 ? n_my - 2 : 0); ti < n_my; ++ti) {  // the last tiles' aggregates
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+        const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
+        tma_store_3d(&tmOut, src, 0, t * 128, b);
+        tma_store_3d(&tmOut, src + BLK, 32, t * 128, b);
+        bulk_commit();
+      }
+      bulk_wait0();
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, 64);
+      mbar_wait(bar_w, 0);
+      mbar_wait(bar_wscaled, 0);
+      const uint64_t desc_w1e = umma_desc(sbase + OFF_W1E);
+      const uint64_t desc_w1r = umma_desc(sbase + OFF_W1R);
+      const uint64_t desc_w2 = umma_desc(sbase + OFF_W2);
+      const uint64_t desc_ring = umma_desc(sbase + OFF_RING);
+      const int n_items = n_my * (d + 1);
+      int item = 0, m = 0, gr = 0, g1 = 0, g2 = 0;
+      uint32_t idle = 0;
+      while (g2 < n_sub) {
+        bool progress = false;
+        if (item < n_items) {
+          const int slot = item % NR;
+          const uint64_t a0 = desc_ring + (uint64_t)((slot * 2 * BLK) >> 4);
+          if (m == 0) {
+            // receiver term of tile gr.  Its TMEM buffer was last read by the epilogue 1 of tile gr-2, which is
+            // over once the second GEMM of that tile's last sub-tile has been issued.
+            if (g2 >= (gr - 1) * d && mbar_test(bar_ring_full + 8 * slot, (uint32_t)((item / NR) & 1))) {
+              tc_fence_after();
+              const uint32_t dr = tmem_base + (gr & 1) * 64;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_tf32(dr, a0 + (uint64_t)((jj * BLK) >> 4) + 2 * kk, desc_w1r + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc,
+                            (uint32_t)((jj | kk) != 0));
+              umma_commit(bar_dr_full + 8 * (gr & 1));
+              umma_commit(bar_ring_free + 8 * slot);
+              ++gr;
+              ++item;
+              m = 1;
+              progress = true;
+            }
+          } else if (g1 <= g2 + 1) {
+            const int j = g1, ts = j & 1;
+            if (mbar_test(bar_ring_full + 8 * slot, (uint32_t)((item / NR) & 1)) &&
+                mbar_test(bar_d_free + 8 * ts, (uint32_t)(((j >> 1) & 1) ^ 1))) {
+              tc_fence_after();
+              E3_DBG(8, j);
+              const uint32_t dd = tmem_base + 128 + ts * 128;
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_tf32(dd, a0 + (uint64_t)((jj * BLK) >> 4) + 2 * kk, desc_w1e + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc,
+                            (uint32_t)((jj | kk) != 0));
+              umma_commit(bar_d1_full + 8 * ts);
+              umma_commit(bar_ring_free + 8 * slot);
+              E3_DBG(1, j);
+              ++g1;
+              ++item;
+              m = (m == d) ? 0 : m + 1;
+              progress = true;
+            }
+          }
+        }
+        if (g2 < g1) {
+          const int j = g2, ts = j & 1;
+          if (mbar_test(bar_hb_full + 8 * ts, (uint32_t)((j >> 1) & 1))) {
+            tc_fence_after();
+            E3_DBG(9, j);
+            const uint32_t dd = tmem_base + 128 + ts * 128;
+            const uint32_t ht = dd + 64;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_tf32_ts(dd, ht + (uint32_t)(jj * 32 + kk * 8), desc_w2 + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc,
+                             (uint32_t)((jj | kk) != 0));
+            umma_commit(bar_d2_full + 8 * ts);
+            E3_DBG(2, j);
+            ++g2;
+            progress = true;
+          }
+        }
+        if (progress) idle = 0;
+        else if (++idle > (1u << 26)) {
+          printf("nlam tc_ell_window: MMA issuer timeout (block %d item %d g1 %d g2 %d)\n", blockIdx.x, item, g1, g2);
+          __trap();
+        }
+      }
+    }
+  } else if (warp >= W_E1) {
+    // =============================== epilogue 1 (8 warps: thread = row x 32 columns) ===============================
+    const bool lead = warp == W_E1;
+    const int q = warp & 3;
+    const int half = (warp - W_E1) >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = half * 32;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    // window row of this thread's edge in sub-tile j (prefetched one sub-tile ahead)
+    auto load_loc = [&](int j) -> int {
+      if (j >= n_sub) return 0;
+      const int ti = j / d, k = j - ti * d;
+      const int w = blockIdx.x + ti * gridDim.x;
+      const int t = w % p.n_tiles;
+      const long long r = (long long)t * 128 + row;
+      return (r < p.n_rec) ? (int)__ldg(p.loc + r * d + k) : 0;
+    };
+    // SiLU(z) = h + h*tanh(h) with h = z/2: halve the first-Linear weight tiles once (exact), so the GEMMs
+    // deliver h's terms directly; the gathered sender term (which carries b1) is halved in the FMA below
+    {
+      mbar_wait(bar_w, 0);
+      float4* wq = reinterpret_cast<float4*>(smem + OFF_W1E) + (tid - W_E1 * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // W1e | W1r: 32 KB = 2048 float4 over 256 threads
+        float4 x = wq[i * E1_THREADS];
+        x.x *= 0.5f;
+        x.y *= 0.5f;
+        x.z *= 0.5f;
+        x.w *= 0.5f;
+        wq[i * E1_THREADS] = x;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_wscaled);
+    }
+    const float2 half2 = make_float2(0.5f, 0.5f);
+    int loc_next = load_loc(0);
+    int ti = 0, k = 0;
+    for (int j = 0; j < n_sub; ++j) {
+      const int ts = j & 1;
+      const int loc = loc_next;
+      loc_next = load_loc(j + 1);
+      if (lead) {
+        if (k == 0) {
+          mbar_wait(bar_dr_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+          mbar_wait(bar_win_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+        }
+        mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((j >> 1) & 1));
+      }
+      named_bar_sync(1, E1_THREADS);
+      tc_fence_after();
+      if (lead && lane == 0) E3_DBG(3, j);
+      const uint8_t* ps = smem + OFF_WIN + (ti & 1) * 2 * BLK + half * BLK + loc * 128;
+      const int rx = loc & 7;
+      const uint32_t d1 = tmem_base + 128 + ts * 128 + t_lane + c0;
+      const uint32_t dr = tmem_base + (ti & 1) * 64 + t_lane + c0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[16], r[16];
+        tmem_ld16(d1 + c * 16, v);
+        tmem_ld16(dr + c * 16, r);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(ps + (((c * 4 + k4) ^ rx) << 4));
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float2 sv = u ? make_float2(s4.z, s4.w) : make_float2(s4.x, s4.y);
+            const float2 h = fma2(sv, half2, add2(make_float2(v[4 * k4 + 2 * u], v[4 * k4 + 2 * u + 1]),
+                                                  make_float2(r[4 * k4 + 2 * u], r[4 * k4 + 2 * u + 1])));
+            const float2 o = fma2(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
+            v[4 * k4 + 2 * u] = o.x;
+            v[4 * k4 + 2 * u + 1] = o.y;
+          }
+        }
+        tmem_st16(d1 + 64 + c * 16, v);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_hb_full + 8 * ts);
+      if (lead && lane == 0) E3_DBG(4, j);
+      if (++k == d) {
+        k = 0;
+        ++ti;
+      }
+    }
+  } else {
+    // =============================== epilogue 2 (8 warps; accumulates the d sub-tiles in registers) ===============
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = half * 32;
+    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
+    const int pbar = 4 + q;
+    const uint32_t ln_col = tmem_base + 384 + t_lane;
+    // aggregate = gamma * sum_k (v_k - mu_k) * rstd_k + d * beta: accumulate sum_k v_k*rstd_k per column and
+    // sum_k mu_k*rstd_k per row; gamma / beta are applied once per tile
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.f, 0.f);
+    float mr = 0.f;
+    int j = 0;
+    for (int ti = 0; ti < n_my; ++ti) {
+      for (int k = 0; k < d; ++k, ++j) {
+        const int ts = j & 1;
+        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((j >> 1) & 1));
+        if (tid == 0) E3_DBG(5, j);
+        named_bar_sync(2, G2_THREADS);
+        tc_fence_after();
+        if (tid == 0) E3_DBG(6, j);
+        float vf[32];
+        tmem_ld32(tmem_base + 128 + ts * 128 + t_lane + c0, vf);
+        tc_fence_before();
+        mbar_arrive(bar_d_free + 8 * ts);
+        float2 v[16];
+        float2 sm2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const float4 bb = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k8);
+          v[2 * k8] = add2(make_float2(vf[4 * k8], vf[4 * k8 + 1]), make_float2(bb.x, bb.y));
+          v[2 * k8 + 1] = add2(make_float2(vf[4 * k8 + 2], vf[4 * k8 + 3]), make_float2(bb.z, bb.w));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          sm2 = add2(sm2, v[i]);
+          sq2 = fma2(v[i], v[i], sq2);
+        }
+        tmem_st2(ln_col + 2 * half, sm2.x + sm2.y, sq2.x + sq2.y);
+        tc_fence_before();
+        named_bar_sync(pbar, 64);
+        tc_fence_after();
+        float st4[4];
+        tmem_ld4(ln_col, st4);
+        const float mu = (st4[0] + st4[2]) * (1.0f / 64.0f);
+        const float ex2 = (st4[1] + st4[3]) * (1.0f / 64.0f);
+        const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
+        const float2 rs2 = make_float2(rstd, rstd);
+        mr = fmaf(mu, rstd, mr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma2(v[i], rs2, acc[i]);
+        // the pair barrier also orders this sub-tile's scratch reads before the next sub-tile's writes
+        named_bar_sync(pbar, 64);
+        if (tid == 0) E3_DBG(7, j);
+      }
+      // stage the aggregate in the tile's sender window (every epilogue 1 of the tile is over: the second GEMMs
+      // are issued in order, each after its epilogue 1); the gather warp stores it with TMA (rows past the end
+      // of the tensor are clipped) before it refills the buffer
+      {
+        const float sc = p.mean ? 1.0f / (float)d : 1.0f;
+        const float bsc = p.mean ? 1.0f : (float)d;
+        uint8_t* orow = smem + OFF_WIN + (ti & 1) * 2 * BLK + half * BLK + row * 128;
+        const int rx = row & 7;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const float4 g4 = *reinterpret_cast<const float4*>(sprm + 128 + c0 + 4 * k8);
+          const float4 b4 = *reinterpret_cast<const float4*>(sprm + 192 + c0 + 4 * k8);
+          float4 o;
+          o.x = fmaf((acc[2 * k8].x - mr) * sc, g4.x, bsc * b4.x);
+          o.y = fmaf((acc[2 * k8].y - mr) * sc, g4.y, bsc * b4.y);
+          o.z = fmaf((acc[2 * k8 + 1].x - mr) * sc, g4.z, bsc * b4.z);
+          o.w = fmaf((acc[2 * k8 + 1].y - mr) * sc, g4.w, bsc * b4.w);
+          *reinterpret_cast<float4*>(orow + ((k8 ^ rx) << 4)) = o;
+          acc[2 * k8] = acc[2 * k8 + 1] = make_float2(0.f, 0.f);
+        }
+        mr = 0.f;
+        fence_proxy_async();
+        mbar_arrive(bar_staged + 8 * (ti & 1));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------ host
 int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const float* wslice, int ldw, const float* bias,
               float* out, cudaStream_t st);  // tc2.cu
@@ -429,12 +907,12 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   const int64_t ns = g->n_send, nr = g->n_rec;
   float* Ps = ws;
   const float* w1 = edge_mlp->w[0];
-  int rc = rowlinear(send, send_bs, ns, Bs, w1 + 64, 192, nullptr, Ps, st);
+  int rc = rowlinear(send, send_bs, ns, Bs, w1 + 64, 192, edge_mlp->b[0], Ps, st);  // P_s carries b1
   if (rc) return rc;
 
   EncodeTiledFn enc = get_encode();
   NLAM_REQUIRE(enc, NLAM_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  CUtensorMap me, mrec, mw1, mw2, mps;
+  CUtensorMap me, mrec, mw1, mw2, mps, mo;
   {
     // edge tensor (B, n_rec, d, 64): box = 32 columns x 1 slot x 128 receivers
     const bool batched = edge_bs != 0 && B > 1;
@@ -456,6 +934,8 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   rc = make_map(&mw2, edge_mlp->w[1], 64, 64, 1, 64, 0, 64, false);
   if (rc) return rc;
   rc = make_map(&mps, Ps, 64, (uint64_t)ns * Bs, 1, 64, 0, 1, false);
+  if (rc) return rc;
+  rc = make_map(&mo, aggr_out, 64, (uint64_t)nr, (uint64_t)B, 64, (uint64_t)nr * 64, 128, true);
   if (rc) return rc;
   EllParams p;
   memset(&p, 0, sizeof(p));
@@ -484,6 +964,9 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   const long long n_work = (long long)p.n_tiles * p.B;
   NLAM_REQUIRE(n_work * d < (1LL << 31) - 4096, NLAM_E_UNSUPPORTED, "tc_ell_edge: too many work items");
   const int grid = (int)std::min<long long>(n_work, num_sms());
+  static int use_window = -1;
+  if (use_window < 0) use_window = getenv("NLAM_TC_ELL_NO_WINDOW") ? 0 : 1;
+  const bool window = use_window && g->ell_window;
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("NLAM_TC_TIMELINE") ? 1 : 0;
@@ -492,7 +975,39 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-  tc_ell_edge_kernel<<<grid, e3::THREADS, e3::SMEM, st>>>(me, mrec, mw1, mw2, mps, p);
+  if (window) {
+    static unsigned attr_mask_w = 0;
+    if (!(attr_mask_w & (1u << (dev & 31)))) {
+      NLAM_CUDA_OK(cudaFuncSetAttribute(tc_ell_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e4::SMEM));
+      attr_mask_w |= 1u << (dev & 31);
+    }
+    EllWinParams q;
+    memset(&q, 0, sizeof(q));
+    q.win_u = g->ell_u;
+    q.win_nu = g->ell_nu;
+    q.loc = g->ell_loc;
+    q.d = d;
+    q.ps_rows = p.ps_rows;
+    q.b1 = p.b1;
+    q.b2 = p.b2;
+    q.gamma = p.gamma;
+    q.beta = p.beta;
+    q.eps = p.eps;
+    q.aggr = p.aggr;
+    q.e_batched = p.e_batched;
+    q.rec_batched = p.rec_batched;
+    q.mean = p.mean;
+    q.n_rec = p.n_rec;
+    q.B = p.B;
+    q.n_tiles = p.n_tiles;
+    q.dbg = p.dbg;
+    static int pf = -1;
+    if (pf < 0) pf = getenv("NLAM_ELL_NO_PREFETCH") ? 0 : 1;
+    q.prefetch = pf;
+    tc_ell_window_kernel<<<grid, e4::THREADS, e4::SMEM, st>>>(me, mrec, mw1, mw2, mps, mo, q);
+  } else {
+    tc_ell_edge_kernel<<<grid, e3::THREADS, e3::SMEM, st>>>(me, mrec, mw1, mw2, mps, p);
+  }
   count_launch();
   if (dbg_on) {
     long long h[256];
@@ -500,10 +1015,10 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     NLAM_CUDA_OK(cudaStreamSynchronize(st));
     long long t0 = h[0];
     fprintf(stderr, "[nlam tc_ell timeline] grid=%d tiles=%lld d=%d (cycles rel. to first stage issue)\n", grid, n_work, d);
-    fprintf(stderr, "  j  ld_iss  g1_iss  g2_iss e1_start e1_done e2_wait e2_start e2_done\n");
+    fprintf(stderr, "  j  ld_iss  g1_iss  g2_iss e1_start e1_done e2_wait e2_start e2_done  g1_beg  g2_beg\n");
     for (int it = 0; it < 16; ++it) {
       fprintf(stderr, "%3d ", it);
-      for (int k = 0; k < 8; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+      for (int k = 0; k < 10; ++k) fprintf(stderr, "%7lld ", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }

@@ -176,6 +176,8 @@ class Graph:
         self.n_send = L.nlam_graph_num_send(h)
         self.max_in_degree = L.nlam_graph_max_in_degree(h)
         self.is_sorted = bool(L.nlam_graph_is_sorted(h))
+        self.uniform_degree = L.nlam_graph_uniform_degree(h)
+        self.ell_window = L.nlam_graph_ell_window(h)
         self.perm = L.nlam_graph_perm(h)
         self.inv_perm = L.nlam_graph_inv_perm(h)
 

@@ -45,6 +45,8 @@ check("d=2 B=1", 100, 129, 2, 1)
 check("d=3 expand edge", 64, 500, 3, 3, expand_edge=True)
 check("d=8 bcast rec", 64, 300, 8, 2, bcast_rec=True)
 check("d=5 multi-tile per CTA", 2000, 128 * 150 + 17, 5, 2)
+check("d=4 window multi-tile per CTA", 120, 128 * 150 + 17, 4, 2)
+check("d=1 window multi-tile", 5000, 128 * 300 + 5, 1, 3, aggr="mean")
 
 spec = synthetic.make_graph_spec(238, 268)
 ei = spec["m2g_edge_index"]

@@ -232,3 +232,64 @@ print("LAUNCHES", nlb._lib.lib().nlam_launch_count())
         outs[mode] = int([l for l in r.stdout.splitlines() if l.startswith("LAUNCHES")][0].split()[1])
     # v2 issues two extra node-projection launches per InteractionNet call
     assert outs["v2"] == outs["v1"] + 2 * 2
+
+
+def _ell_graph(ns, nr, d, seed):
+    """Every receiver has exactly d incoming edges (mesh->grid: d = 4, mesh-down: d = 1)."""
+    g = torch.Generator().manual_seed(seed)
+    rcv = torch.arange(nr).repeat_interleave(d)
+    snd = torch.randint(0, ns, (nr * d,), generator=g)
+    return torch.stack([snd, rcv])
+
+
+ELL_CASES = [
+    # name, ns, nr, d, B, aggr, expanded edge, broadcast receivers
+    # few senders -> every tile's distinct senders fit one 128-row window (windowed kernel)
+    ("win_d4", 50, 30, 4, 2, "sum", False, False),
+    ("win_d4_mean_tail", 100, 1000, 4, 3, "mean", False, False),
+    ("win_d1_always", 5000, 128 * 20 + 5, 1, 2, "sum", False, False),
+    ("win_d8_bcast_rec", 64, 300, 8, 2, "sum", False, True),
+    ("win_multi_tile_per_cta", 120, 128 * 150 + 17, 4, 2, "sum", True, False),
+    # many random senders -> more than 128 distinct senders per tile (per-sub-tile gather kernel)
+    ("gather_d5", 2000, 128 * 150 + 17, 5, 2, "sum", False, False),
+    ("gather_d2_B1", 4000, 129, 2, 1, "mean", False, False),
+    ("gather_d3_expand", 3000, 500, 3, 3, "sum", True, False),
+]
+
+
+@pytest.mark.parametrize("case", ELL_CASES, ids=[c[0] for c in ELL_CASES])
+def test_uniform_degree_edge_kernels_vs_oracle(case):
+    """Uniform in-degree edge sets with update_edges=False take the receiver-tiled kernels of tc3.cu."""
+    name, ns, nr, d, B, aggr, expand, bcast = case
+    ei = _ell_graph(ns, nr, d, 1)
+    torch.manual_seed(0)
+    net = nlb.InteractionNet(ei, 64, update_edges=False, aggr=aggr, math="tf32")
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    send = torch.randn(B, ns, 64)
+    rec = torch.randn(1 if bcast else B, nr, 64)
+    edge = torch.randn(1 if expand else B, nr * d, 64)
+    sd = dict(net.state_dict())
+    sd64 = {k: v.double() for k, v in sd.items()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+
+    def f64():
+        return rp.interaction_net(sd64, ei, send.double(), rec.double().expand(B, -1, -1),
+                                  edge.double().expand(B, -1, -1), aggr=aggr, update_edges=False)
+
+    def fgpu():
+        return rp.interaction_net(sdg, ei.to(DEV), send.to(DEV), rec.to(DEV).expand(B, -1, -1),
+                                  edge.to(DEV).expand(B, -1, -1), aggr=aggr, update_edges=False)
+
+    ref_err, want = _ref_tf32_err(f64, fgpu)
+    net = net.to(DEV)
+    graph = net._graph(next(net.parameters()).device)
+    assert graph.uniform_degree == d
+    assert graph.ell_window == (1 if name.startswith("win") else 0)
+    with torch.no_grad():
+        got = net(send.to(DEV), rec.to(DEV).expand(B, -1, -1), edge.to(DEV).expand(B, -1, -1))
+    err = (got.double().cpu() - want[0]).abs().max().item()
+    assert err <= ABS_TOL, (name, err)
+    assert err <= max(3 * ref_err, 4e-3), (name, err, ref_err)
