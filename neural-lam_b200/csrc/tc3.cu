@@ -701,7 +701,7 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
           }
         }
         if (progress) idle = 0;
-        else if (++idle > (1u << 26)) {
+        else if (__nanosleep(40), ++idle > (1u << 24)) {  // idle polling must not take issue slots from the epilogue warps
           printf("nlam tc_ell_window: MMA issuer timeout (block %d item %d g1 %d g2 %d)\n", blockIdx.x, item, g1, g2);
           __trap();
         }
