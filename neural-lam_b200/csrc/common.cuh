@@ -45,6 +45,10 @@ size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_ma
 int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, int64_t send_rows, float* ws);
+// tc4.cu
+bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
+int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
+                int B, cudaStream_t stream);
 // tc3.cu
 bool tc_ell_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                       const float* rec, int64_t rec_bs, bool has_edge_out);

@@ -793,6 +793,8 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
   int nout = 0;
   NLAM_REQUIRE(mlp_shape_ok(mlp, &nout), NLAM_E_UNSUPPORTED, "tc_rowmlp: unsupported MLP shape");
   NLAM_REQUIRE(aligned16(out), NLAM_E_INVALID, "tc_rowmlp: output not 16-byte aligned");
+  // dense 64-wide inputs, LayerNorm output: the streaming kernel of tc4.cu
+  if (tc_rowmlp64_supported(mlp, srcs, n_src, res, n_rows)) return tc_rowmlp64(mlp, srcs, n_src, res, out, n_rows, B, st);
   TcParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap a0, a1, w1, w2;
