@@ -70,8 +70,10 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
     } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows) && workspace &&
         ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
       // split first Linear: node projections + K=64 edge kernel (tc2.cu)
-      rc = tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows,
-                    (float*)((char*)workspace + msg_bytes + agg_bytes));
+      float* proj = (float*)((char*)workspace + msg_bytes + agg_bytes);
+      rc = tc_edge3_enabled()
+               ? tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, proj)
+               : tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows, proj);
     } else {
       rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
     }

@@ -45,6 +45,11 @@ size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_ma
 int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, int64_t send_rows, float* ws);
+// tc5.cu
+bool tc_edge3_enabled();
+int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+             int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
+             cudaStream_t stream, float* ws);
 // tc4.cu
 bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
 int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
@@ -86,6 +91,11 @@ struct NlamGraph {
   int32_t* ell_u = nullptr;
   int32_t* ell_nu = nullptr;
   uint8_t* ell_loc = nullptr;
+  // sender windows of the CSR tiles (tc2.cu): the 128-edge window of tile t reads win_nu[t] <= 128 distinct
+  // senders win_u[128*t ..] (ascending, padded to a multiple of 4); its row i reads window row win_loc[128*t + i]
+  int32_t* win_u = nullptr;
+  int32_t* win_nu = nullptr;
+  uint8_t* win_loc = nullptr;
   std::vector<int32_t> h_tile_rec, h_rowptr;
 };
 

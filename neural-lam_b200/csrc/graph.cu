@@ -120,6 +120,29 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
     tile_meta.push_back(tile_rec[i]);
     tile_meta.push_back(tile_rec[i + 1] - tile_rec[i]);
   }
+  // sender windows of the CSR tiles (tc2.cu): tile t works on the 128-edge window [e0, e0+128) (the edges past
+  // its own are recomputed identically by the following tiles), which reads <= 128 distinct senders
+  std::vector<int32_t> win_u, win_nu;
+  std::vector<uint8_t> win_loc;
+  if (g->n_tiles > 0) {
+    const int64_t nt = g->n_tiles;
+    win_u.assign((size_t)nt * 128, 0);
+    win_nu.assign((size_t)nt, 0);
+    win_loc.assign((size_t)nt * 128, 0);
+    std::vector<int32_t> u;
+    for (int64_t t = 0; t < nt; ++t) {
+      const int64_t k0 = tile_e0[t], k1 = std::min<int64_t>(E, k0 + 128);
+      if (k1 <= k0) continue;
+      u.assign(src.begin() + k0, src.begin() + k1);
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      for (int64_t k = k0; k < k1; ++k)
+        win_loc[(size_t)t * 128 + (k - k0)] = (uint8_t)(std::lower_bound(u.begin(), u.end(), src[k]) - u.begin());
+      const size_t nu = (u.size() + 3) / 4 * 4;
+      for (size_t i = 0; i < nu; ++i) win_u[(size_t)t * 128 + i] = u[std::min(i, u.size() - 1)];
+      win_nu[t] = (int32_t)nu;
+    }
+  }
   // sender windows of the ELL kernel (tc3.cu)
   std::vector<int32_t> ell_u, ell_nu;
   std::vector<uint8_t> ell_loc;
@@ -174,7 +197,8 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
       (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
       (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0)) ||
       (rc = upload(&g->tile_meta, tile_meta)) || (rc = upload(&g->ell_u, ell_u)) ||
-      (rc = upload(&g->ell_nu, ell_nu)) || (rc = upload(&g->ell_loc, ell_loc))) {
+      (rc = upload(&g->ell_nu, ell_nu)) || (rc = upload(&g->ell_loc, ell_loc)) ||
+      (rc = upload(&g->win_u, win_u)) || (rc = upload(&g->win_nu, win_nu)) || (rc = upload(&g->win_loc, win_loc))) {
     cudaSetDevice(prev_dev);
     nlam_graph_destroy(g);
     return rc;
@@ -202,6 +226,9 @@ extern "C" void nlam_graph_destroy(NlamGraph* g) {
   cudaFree(g->ell_u);
   cudaFree(g->ell_nu);
   cudaFree(g->ell_loc);
+  cudaFree(g->win_u);
+  cudaFree(g->win_nu);
+  cudaFree(g->win_loc);
   cudaSetDevice(prev);
   delete g;
 }

@@ -45,7 +45,9 @@ constexpr uint32_t SMEM = OFF_MISC + 3072;       // 232448
 }  // namespace e2
 
 struct Edge2Params {
-  const int32_t* src;       // CSR-ordered sender ids
+  const int32_t* win_u;     // per tile: 128 distinct sender ids of its edge window
+  const int32_t* win_nu;    // per tile: window rows (multiple of 4)
+  const uint8_t* win_loc;   // per tile: window row of each of the 128 edge rows
   const int32_t* dst;       // CSR-ordered receiver ids
   int ps_rows;              // rows of one batch in the P_s gather map (0: batch-broadcast)
   const float* pr;          // P_r (B_r, n_rec, 64)
@@ -94,6 +96,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
   const uint32_t bar_hb_full = mb + 72;   // [2] hidden written (128 arrivals)
   const uint32_t bar_d2_full = mb + 88;   // [2]
   const uint32_t bar_d_free = mb + 104;   // [2] D2 drained into registers (256 arrivals)
+  const uint32_t bar_wscaled = mb + 1192;  // W1e halved in place (256 arrivals); after the CSR offset arrays
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 120);
   int* lp_all = reinterpret_cast<int*>(smem + OFF_MISC + 128);  // [2 groups][132] local CSR offsets
   float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 2048);  // b2 | gamma | beta (64 floats each):
@@ -104,6 +107,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
   if (warp == W_MMA) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
+      mbar_init(bar_wscaled, 2 * E1_THREADS);
       for (int s = 0; s < NS; ++s) {
         mbar_init(bar_full + 8 * s, 1);
         mbar_init(bar_epi_done + 8 * s, 1);
@@ -155,12 +159,13 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     const int op = lw * 22 + lane;
     const int grp4 = op & 31, jb = (op >> 5) & 1;
     const bool issuer = lane < 22 && op < 64;
-    int idx[4] = {0, 0, 0, 0};
-    if ((int)blockIdx.x < n_work && issuer) {
-      const int e0 = p.tile_e0[(int)blockIdx.x % p.n_tiles];
-      const int win = (int)min((long long)BM, p.n_edges - e0);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) idx[u] = (4 * grp4 + u < win) ? __ldg(p.src + e0 + 4 * grp4 + u) : 0;
+    // the window's distinct senders (prefetched one tile ahead): ngrp groups of 4 rows
+    int4 ids = make_int4(0, 0, 0, 0);
+    int ngrp = 0;
+    if ((int)blockIdx.x < n_work) {
+      const int t0 = (int)blockIdx.x % p.n_tiles;
+      ngrp = __ldg(p.win_nu + t0) >> 2;
+      if (issuer && grp4 < ngrp) ids = __ldg(reinterpret_cast<const int4*>(p.win_u + (size_t)t0 * 128) + grp4);
     }
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -173,7 +178,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
         if (lane == 0) {
           mbar_wait(bar_epi_done + 8 * s, sph ^ 1);  // tile it-3 released the stage
           E2_DBG(0, it);
-          mbar_expect_tx(full, 4u * BLK);
+          mbar_expect_tx(full, 2u * BLK + (uint32_t)ngrp * 1024u);
           const int e0 = p.tile_e0[t];
           tma_load_3d(stg, &tmE, full, 0, e0, p.e_batched ? b : 0, pol_stream);
           tma_load_3d(stg + BLK, &tmE, full, 32, e0, p.e_batched ? b : 0, pol_stream);
@@ -181,17 +186,17 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
         __syncwarp();
       }
       named_bar_sync(12, LD_THREADS);  // stage free + transaction count armed
-      if (issuer) {
+      if (issuer && grp4 < ngrp) {
         const int boff = p.ps_rows * b;
-        // rows past the end of the edge list gather row 0 (never stored)
-        tma_gather4(stg + (2 + jb) * BLK + grp4 * 512, &tmPs, full, 32 * jb, idx[0] + boff, idx[1] + boff, idx[2] + boff,
-                    idx[3] + boff, pol_keep);
+        tma_gather4(stg + (2 + jb) * BLK + grp4 * 512, &tmPs, full, 32 * jb, ids.x + boff, ids.y + boff, ids.z + boff,
+                    ids.w + boff, pol_keep);
+      }
+      {
         const int wn = w + (int)gridDim.x;
         if (wn < n_work) {
-          const int e0n = p.tile_e0[wn % p.n_tiles];
-          const int win = (int)min((long long)BM, p.n_edges - e0n);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) idx[u] = (4 * grp4 + u < win) ? __ldg(p.src + e0n + 4 * grp4 + u) : 0;
+          const int tn = wn % p.n_tiles;
+          ngrp = __ldg(p.win_nu + tn) >> 2;
+          if (issuer && grp4 < ngrp) ids = __ldg(reinterpret_cast<const int4*>(p.win_u + (size_t)tn * 128) + grp4);
         }
       }
       if (lw == 0 && lane == 0) {
@@ -211,6 +216,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       int n_my = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
       mbar_wait(bar_w, 0);
+      mbar_wait(bar_wscaled, 0);
       const uint64_t desc_w1 = umma_desc(sbase + OFF_W1);
       const uint64_t desc_w2 = umma_desc(sbase + OFF_W2);
       const uint64_t desc_st = umma_desc(sbase + OFF_ST);
@@ -257,7 +263,7 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
           }
         }
         if (progress) idle = 0;
-        else if (++idle > (1u << 26)) {
+        else if (__nanosleep(40), ++idle > (1u << 24)) {  // idle polling must not take issue slots from the epilogues
           printf("nlam tc_edge2: MMA issuer timeout (block %d g1 %d g2 %d)\n", blockIdx.x, g1, g2);
           __trap();
         }
@@ -272,24 +278,44 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    const uint32_t rsw = (uint32_t)(row * 128);
-    const int rx = row & 7;
     const int stride1 = 2 * (int)gridDim.x;
     const int w_first1 = (int)blockIdx.x + g1g * (int)gridDim.x;
-    int dst_next = 0;
+    // SiLU(z) = h + h*tanh(h), h = z/2: W1e is halved in place once (exact); the gathered node terms are halved
+    // in the FMA that adds them
+    {
+      mbar_wait(bar_w, 0);
+      float4* wq = reinterpret_cast<float4*>(smem + OFF_W1) + (tid - W_E1 * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 16 KB = 1024 float4 over 256 threads
+        float4 x = wq[i * 2 * E1_THREADS];
+        x.x *= 0.5f;
+        x.y *= 0.5f;
+        x.z *= 0.5f;
+        x.w *= 0.5f;
+        wq[i * 2 * E1_THREADS] = x;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_wscaled);
+    }
+    const float2 half2 = make_float2(0.5f, 0.5f);
+    int dst_next = 0, loc_next = 0;
     if (w_first1 < n_work) {
-      const int e0 = p.tile_e0[w_first1 % p.n_tiles];
+      const int t0 = w_first1 % p.n_tiles;
+      const int e0 = p.tile_e0[t0];
       dst_next = (e0 + row < p.n_edges) ? __ldg(p.dst + e0 + row) : 0;
+      loc_next = __ldg(p.win_loc + (size_t)t0 * 128 + row);
     }
     int it = g1g;
     for (int w = w_first1; w < n_work; w += stride1, it += 2) {
       const int b = w / p.n_tiles;
       const int ts = it & 1, s = it % NS;
-      const int my_dst = dst_next;
+      const int my_dst = dst_next, loc = loc_next;
       const int wn = w + stride1;
       if (wn < n_work) {
-        const int e0n = p.tile_e0[wn % p.n_tiles];
+        const int tn = wn % p.n_tiles;
+        const int e0n = p.tile_e0[tn];
         dst_next = (e0n + row < p.n_edges) ? __ldg(p.dst + e0n + row) : 0;
+        loc_next = __ldg(p.win_loc + (size_t)tn * 128 + row);
       }
       // receiver projection row of this edge: rows of one CSR segment share it, so the lanes' loads
       // coalesce to one request per distinct receiver
@@ -304,7 +330,8 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       named_bar_sync(g1bar, E1_THREADS);
       tc_fence_after();
       if (g1lead && lane == 0) E2_DBG(6, it);
-      const uint8_t* ps = smem + OFF_ST + s * 4 * BLK + 2 * BLK + rsw;
+      const uint8_t* ps = smem + OFF_ST + s * 4 * BLK + 2 * BLK + loc * 128;  // this edge's row of the sender window
+      const int rx = loc & 7;
       const uint32_t d1 = tmem_base + ts * 128 + t_lane;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -319,10 +346,16 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float4 s4 = *reinterpret_cast<const float4*>(psb + ((((c & 1) * 4 + k) ^ rx) << 4));
-          v[4 * k + 0] = silu_fast(v[4 * k + 0] + s4.x + pr_cur[k].x);
-          v[4 * k + 1] = silu_fast(v[4 * k + 1] + s4.y + pr_cur[k].y);
-          v[4 * k + 2] = silu_fast(v[4 * k + 2] + s4.z + pr_cur[k].z);
-          v[4 * k + 3] = silu_fast(v[4 * k + 3] + s4.w + pr_cur[k].w);
+          const float2 h0 = fma2(add2(make_float2(s4.x, s4.y), make_float2(pr_cur[k].x, pr_cur[k].y)), half2,
+                                 make_float2(v[4 * k + 0], v[4 * k + 1]));
+          const float2 h1 = fma2(add2(make_float2(s4.z, s4.w), make_float2(pr_cur[k].z, pr_cur[k].w)), half2,
+                                 make_float2(v[4 * k + 2], v[4 * k + 3]));
+          const float2 o0 = fma2(h0, make_float2(tanh_fast(h0.x), tanh_fast(h0.y)), h0);
+          const float2 o1 = fma2(h1, make_float2(tanh_fast(h1.x), tanh_fast(h1.y)), h1);
+          v[4 * k + 0] = o0.x;
+          v[4 * k + 1] = o0.y;
+          v[4 * k + 2] = o1.x;
+          v[4 * k + 3] = o1.y;
         }
         tmem_st16(d1 + 64 + c * 16, v);
         if (c < 3) {
@@ -378,28 +411,27 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       named_bar_sync(gbar, G2_THREADS);
       tc_fence_after();
       if (gt == 0) E2_DBG(8, it);
-      float v[32];
-      tmem_ld32(tmem_base + grp * 128 + t_lane + c0, v);
+      float vf[32];
+      tmem_ld32(tmem_base + grp * 128 + t_lane + c0, vf);
       tc_fence_before();
       mbar_arrive(bar_d_free + 8 * grp);  // the TMEM stage may take the next tile's first GEMM
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 bb = *reinterpret_cast<const float4*>(sprm + c0 + 4 * k);
-        v[4 * k + 0] += bb.x;
-        v[4 * k + 1] += bb.y;
-        v[4 * k + 2] += bb.z;
-        v[4 * k + 3] += bb.w;
-      }
+      float2 v[16];
       {
-        // LayerNorm over 64 columns held by two threads (column halves): partial (sum, sum of squares)
-        // parked in spare TMEM columns of the row's lane, one 64-thread barrier, read both back
-        float sm = 0.f, sq = 0.f;
+        // bias, then LayerNorm over 64 columns held by two threads (column halves): partial (sum, sum of
+        // squares) parked in spare TMEM columns of the row's lane, one 64-thread barrier, read both back
+        float2 sm2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          sm += v[i];
-          sq = fmaf(v[i], v[i], sq);
+        for (int k = 0; k < 8; ++k) {
+          const float4 bb = *reinterpret_cast<const float4*>(sprm + c0 + 4 * k);
+          v[2 * k] = add2(make_float2(vf[4 * k], vf[4 * k + 1]), make_float2(bb.x, bb.y));
+          v[2 * k + 1] = add2(make_float2(vf[4 * k + 2], vf[4 * k + 3]), make_float2(bb.z, bb.w));
         }
-        tmem_st2(ln_col + 2 * half, sm, sq);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          sm2 = add2(sm2, v[i]);
+          sq2 = fma2(v[i], v[i], sq2);
+        }
+        tmem_st2(ln_col + 2 * half, sm2.x + sm2.y, sq2.x + sq2.y);
         tc_fence_before();
         named_bar_sync(pbar, 64);
         tc_fence_after();
@@ -408,35 +440,32 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
         const float mu = (st4[0] + st4[2]) * (1.0f / 64.0f);
         const float ex2 = (st4[1] + st4[3]) * (1.0f / 64.0f);
         const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
+        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 g4 = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k);
           const float4 b4 = *reinterpret_cast<const float4*>(sprm + 128 + c0 + 4 * k);
-          v[4 * k + 0] = (v[4 * k + 0] - mu) * rstd * g4.x + b4.x;
-          v[4 * k + 1] = (v[4 * k + 1] - mu) * rstd * g4.y + b4.y;
-          v[4 * k + 2] = (v[4 * k + 2] - mu) * rstd * g4.z + b4.z;
-          v[4 * k + 3] = (v[4 * k + 3] - mu) * rstd * g4.w + b4.w;
+          v[2 * k] = fma2(fma2(v[2 * k], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
+          v[2 * k + 1] = fma2(fma2(v[2 * k + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
         }
       }
       if (gt == 0) E2_DBG(9, it);
-      // messages -> the tile's P_s buffer (consumed by epilogue 1 long ago); e' = e + m in place
+      // messages -> the tile's sender-window buffer (consumed by epilogue 1 long ago); e' = e + m in place
       uint8_t* stg = smem + OFF_ST + s * 4 * BLK;
       {
         uint8_t* mrow = stg + (2 + half) * BLK + rsw;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<float4*>(mrow + ((k ^ rx) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          *reinterpret_cast<float4*>(mrow + ((k ^ rx) << 4)) = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
         if (p.has_out) {
           uint8_t* erow = stg + half * BLK + rsw;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             float4* ptr = reinterpret_cast<float4*>(erow + ((k ^ rx) << 4));
-            float4 r = *ptr;
-            r.x += v[4 * k];
-            r.y += v[4 * k + 1];
-            r.z += v[4 * k + 2];
-            r.w += v[4 * k + 3];
-            *ptr = r;
+            const float4 r = *ptr;
+            const float2 o0 = add2(make_float2(r.x, r.y), v[2 * k]);
+            const float2 o1 = add2(make_float2(r.z, r.w), v[2 * k + 1]);
+            *ptr = make_float4(o0.x, o0.y, o1.x, o1.y);
           }
         }
       }
@@ -488,7 +517,9 @@ tc_edge2_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Node projection: out[b, r, :] = x[b, r, :] · Wsliceᵀ (+ bias), Wslice = 64 x 64 block of a (64, ldw) weight.
+// Node projections: out_i[b, r, :] = x_i[b, r, :] · Wslice_iᵀ (+ bias_i), Wslice = 64 x 64 block of a (64, ldw)
+// weight, for ONE or TWO independent problems in a single launch (the sender and the receiver projection of an
+// edge MLP: one launch and one prologue instead of two, and the tiles of both fill the SMs together).
 // Persistent; per 128-row tile: TMA load (3 stages) -> 8 tcgen05.mma (K = 64) -> epilogue (8 warps: TMEM ->
 // registers, + bias, staged in place in the input tile) -> TMA store.
 // ---------------------------------------------------------------------------------------------------
@@ -498,23 +529,25 @@ constexpr int EPI = 256;
 constexpr int NS = 3;
 constexpr uint32_t BLK = 16384;
 constexpr uint32_t WBLK = 8192;
-constexpr uint32_t OFF_W = 0;
-constexpr uint32_t OFF_ST = 2 * WBLK;
+constexpr uint32_t OFF_W = 0;  // 2 problems x 2 blocks
+constexpr uint32_t OFF_ST = 4 * WBLK;
 constexpr uint32_t OFF_MISC = OFF_ST + NS * 2 * BLK;
 constexpr uint32_t SMEM = OFF_MISC + 1024;
 }  // namespace rl
 
 struct RowLinParams {
-  const float* bias;  // may be null
-  int batched;
-  long long n_rows;
-  int B;
-  int n_tiles;
+  const float* bias[2];  // may be null
+  int batched[2];
+  int n_tiles[2];
+  int n_work0;  // tile-works of problem 0 (tiles x batches); works >= n_work0 belong to problem 1
+  int n_work;
 };
 
 __global__ void __launch_bounds__(rl::THREADS, 1)
-tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmOut, const RowLinParams p) {
+tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmW0,
+                    const __grid_constant__ CUtensorMap tmOut0, const __grid_constant__ CUtensorMap tmX1,
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmOut1,
+                    const RowLinParams p) {
   using namespace rl;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -545,21 +578,27 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int n_work = p.n_tiles * p.B;
+  const int n_work = p.n_work;
+  const bool two = p.n_work0 < n_work;
 
   if (warp == 9) {
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
-      mbar_expect_tx(bar_w, 2u * WBLK);
-      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W + j * WBLK, &tmW, bar_w, 32 * j, 0);
+      mbar_expect_tx(bar_w, (two ? 4u : 2u) * WBLK);
+      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W + j * WBLK, &tmW0, bar_w, 32 * j, 0);
+      if (two)
+        for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W + (2 + j) * WBLK, &tmW1, bar_w, 32 * j, 0);
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int pr = w >= p.n_work0;
+        const int wl = pr ? w - p.n_work0 : w;
+        const int b = wl / p.n_tiles[pr], t = wl - b * p.n_tiles[pr];
         const int s = it % NS;
         mbar_wait(bar_free + 8 * s, (uint32_t)(((it / NS) & 1) ^ 1));
         mbar_expect_tx(bar_full + 8 * s, 2u * BLK);
         for (int j = 0; j < 2; ++j)
-          tma_load_3d(sbase + OFF_ST + (s * 2 + j) * BLK, &tmX, bar_full + 8 * s, 32 * j, t * 128, p.batched ? b : 0, pol);
+          tma_load_3d(sbase + OFF_ST + (s * 2 + j) * BLK, pr ? &tmX1 : &tmX0, bar_full + 8 * s, 32 * j, t * 128,
+                      p.batched[pr] ? b : 0, pol);
       }
     }
   } else if (warp == 8) {
@@ -570,6 +609,7 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const uint64_t desc_st = umma_desc(sbase + OFF_ST);
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int pr = w >= p.n_work0;
         const int s = it % NS, ts = it & 1;
         mbar_wait(bar_full + 8 * s, (uint32_t)((it / NS) & 1));
         mbar_wait(bar_d_free + 8 * ts, (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -579,7 +619,7 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_tf32(tmem_base + ts * 64, desc_st + (uint64_t)(((s * 2 + j) * BLK) >> 4) + 2 * k,
-                      desc_w + (uint64_t)((j * WBLK) >> 4) + 2 * k, idesc, (uint32_t)((j | k) != 0));
+                      desc_w + (uint64_t)(((pr * 2 + j) * WBLK) >> 4) + 2 * k, idesc, (uint32_t)((j | k) != 0));
         umma_commit(bar_d_full + 8 * ts);
       }
     }
@@ -590,8 +630,11 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int rx = row & 7;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+      const int pr = w >= p.n_work0;
+      const int wl = pr ? w - p.n_work0 : w;
+      const int b = wl / p.n_tiles[pr], t = wl - b * p.n_tiles[pr];
       const int s = it % NS, ts = it & 1;
+      const float* bias = p.bias[pr];
       if (warp == 0) mbar_wait(bar_d_full + 8 * ts, (uint32_t)((it >> 1) & 1));
       named_bar_sync(1, EPI);
       tc_fence_after();
@@ -603,8 +646,8 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        if (p.bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * k));
+        if (bias) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * k));
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
         }
         *reinterpret_cast<float4*>(orow + ((k ^ rx) << 4)) = o;  // the MMAs have consumed the input tile
@@ -612,8 +655,9 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       fence_proxy_async();
       named_bar_sync(1, EPI);
       if (tid == 0) {
-        tma_store_3d(&tmOut, sbase + OFF_ST + (s * 2) * BLK, 0, t * 128, b);
-        tma_store_3d(&tmOut, sbase + OFF_ST + (s * 2 + 1) * BLK, 32, t * 128, b);
+        const CUtensorMap* mo = pr ? &tmOut1 : &tmOut0;
+        tma_store_3d(mo, sbase + OFF_ST + (s * 2) * BLK, 0, t * 128, b);
+        tma_store_3d(mo, sbase + OFF_ST + (s * 2 + 1) * BLK, 32, t * 128, b);
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar_free + 8 * s);
@@ -630,23 +674,48 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ host
-int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const float* wslice, int ldw,
-                     const float* bias, float* out, cudaStream_t st) {
-  CUtensorMap mx, mw, mo;
-  const bool batched = B_eff > 1;
-  int rc = make_map(&mx, x, 64, (uint64_t)n_rows, batched ? (uint64_t)B_eff : 1, 64,
-                    batched ? (uint64_t)x_bs : (uint64_t)n_rows * 64, 128, true);
-  if (rc) return rc;
-  rc = make_map(&mw, wslice, 64, 64, 1, (uint64_t)ldw, 0, 64, false);
-  if (rc) return rc;
-  rc = make_map(&mo, out, 64, (uint64_t)n_rows, (uint64_t)B_eff, 64, (uint64_t)n_rows * 64, 128, true);
-  if (rc) return rc;
+struct RowLinProblem {
+  const float* x;
+  int64_t x_bs;
+  int64_t n_rows;
+  int B_eff;
+  const float* wslice;
+  int ldw;
+  const float* bias;
+  float* out;
+};
+
+// one launch for 1 or 2 projection problems
+int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st) {
+  NLAM_REQUIRE(n_prob == 1 || n_prob == 2, NLAM_E_INVALID, "rowlinear_multi: 1 or 2 problems");
+  CUtensorMap mx[2], mw[2], mo[2];
   RowLinParams p;
-  p.bias = bias;
-  p.batched = batched;
-  p.n_rows = n_rows;
-  p.B = B_eff;
-  p.n_tiles = (int)((n_rows + 127) / 128);
+  memset(&p, 0, sizeof(p));
+  long long works[2] = {0, 0};
+  for (int i = 0; i < n_prob; ++i) {
+    const bool batched = pr[i].B_eff > 1;
+    int rc = make_map(&mx[i], pr[i].x, 64, (uint64_t)pr[i].n_rows, batched ? (uint64_t)pr[i].B_eff : 1, 64,
+                      batched ? (uint64_t)pr[i].x_bs : (uint64_t)pr[i].n_rows * 64, 128, true);
+    if (rc) return rc;
+    rc = make_map(&mw[i], pr[i].wslice, 64, 64, 1, (uint64_t)pr[i].ldw, 0, 64, false);
+    if (rc) return rc;
+    rc = make_map(&mo[i], pr[i].out, 64, (uint64_t)pr[i].n_rows, (uint64_t)pr[i].B_eff, 64, (uint64_t)pr[i].n_rows * 64, 128,
+                  true);
+    if (rc) return rc;
+    p.bias[i] = pr[i].bias;
+    p.batched[i] = batched;
+    p.n_tiles[i] = (int)((pr[i].n_rows + 127) / 128);
+    works[i] = (long long)p.n_tiles[i] * pr[i].B_eff;
+  }
+  if (n_prob == 1) {
+    mx[1] = mx[0];
+    mw[1] = mw[0];
+    mo[1] = mo[0];
+    p.n_tiles[1] = 1;
+  }
+  NLAM_REQUIRE(works[0] + works[1] < (1LL << 30), NLAM_E_UNSUPPORTED, "rowlinear: too many work items");
+  p.n_work0 = (int)works[0];
+  p.n_work = (int)(works[0] + works[1]);
   static unsigned attr_mask = 0;
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
@@ -654,20 +723,32 @@ int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const flo
     NLAM_CUDA_OK(cudaFuncSetAttribute(tc_rowlinear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl::SMEM));
     attr_mask |= 1u << (dev & 31);
   }
-  const long long n_work = (long long)p.n_tiles * p.B;
-  NLAM_REQUIRE(n_work < (1LL << 31) - 4096, NLAM_E_UNSUPPORTED, "rowlinear: too many work items");
-  const int grid = (int)std::min<long long>(n_work, num_sms());
-  tc_rowlinear_kernel<<<grid, rl::THREADS, rl::SMEM, st>>>(mx, mw, mo, p);
+  const int grid = (int)std::min<long long>(p.n_work, num_sms());
+  tc_rowlinear_kernel<<<grid, rl::THREADS, rl::SMEM, st>>>(mx[0], mw[0], mo[0], mx[1], mw[1], mo[1], p);
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
 
+int rowlinear(const float* x, int64_t x_bs, int64_t n_rows, int B_eff, const float* wslice, int ldw,
+              const float* bias, float* out, cudaStream_t st) {
+  RowLinProblem pr = {x, x_bs, n_rows, B_eff, wslice, ldw, bias, out};
+  return rowlinear_multi(&pr, 1, st);
+}
+
+// sender and receiver projections of an edge MLP in one launch
+int edge_projections(const float* send, int64_t send_bs, int64_t ns, int Bs, const float* rec, int64_t rec_bs, int64_t nr,
+                     int Br, const float* w1, const float* b1, float* Ps, float* Pr, cudaStream_t st) {
+  RowLinProblem pr[2] = {{send, send_bs, ns, Bs, w1 + 64, 192, nullptr, Ps}, {rec, rec_bs, nr, Br, w1 + 128, 192, b1, Pr}};
+  return rowlinear_multi(pr, 2, st);
+}
+
 bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                         const float* rec, int64_t rec_bs, int B, int64_t send_rows) {
   (void)send_rows;
-  // NLAM_TC_EDGE=v1 | v2 forces one formulation; default: the split kernel where its per-node projection
-  // passes are small next to the edge work (large edge sets such as mesh->grid), the K=192 kernel otherwise
+  // NLAM_TC_EDGE=v1 | v2 forces one formulation; default: the split kernels where the per-node projection
+  // passes are small next to the edge work (mesh graph: ~9 edges per node), the K=192 kernel otherwise
+  // (grid->mesh: projecting every grid node would cost more than gathering raw rows)
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("NLAM_TC_EDGE");
@@ -680,7 +761,7 @@ bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, 
   const double edge_rows = (double)g->n_edges * B;
   const double node_rows = (double)g->n_send * ((send_bs == 0 || B == 1) ? 1 : B) +
                            (double)g->n_rec * ((rec_bs == 0 || B == 1) ? 1 : B);
-  return edge_rows >= 1.0e6 && edge_rows >= 3.0 * node_rows;
+  return edge_rows >= 2.5 * node_rows;
 }
 
 size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_max) {
@@ -702,9 +783,7 @@ int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
   float* Ps = ws;
   float* Pr = ws + (size_t)Bs * ns * 64;
   const float* w1 = edge_mlp->w[0];  // (64, 192): columns [e | sender | receiver]
-  int rc = rowlinear(send, send_bs, ns, Bs, w1 + 64, 192, nullptr, Ps, st);
-  if (rc) return rc;
-  rc = rowlinear(rec, rec_bs, nr, Br, w1 + 128, 192, edge_mlp->b[0], Pr, st);
+  int rc = edge_projections(send, send_bs, ns, Bs, rec, rec_bs, nr, Br, w1, edge_mlp->b[0], Ps, Pr, st);
   if (rc) return rc;
 
   CUtensorMap me, mw1, mw2, mo, mps;
@@ -727,7 +806,9 @@ int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
   if (rc) return rc;
   Edge2Params p;
   memset(&p, 0, sizeof(p));
-  p.src = g->src;
+  p.win_u = g->win_u;
+  p.win_nu = g->win_nu;
+  p.win_loc = g->win_loc;
   p.dst = g->dst;
   p.ps_rows = Bs > 1 ? (int)ns : 0;
   p.pr = Pr;

@@ -248,6 +248,14 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// shared-memory read the compiler may not hoist or keep live across loop iterations (register pressure)
+__device__ __forceinline__ float4 lds128(const void* ptr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(ptr)));
+  return v;
+}
 // packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): one issue slot for two lanes of work
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   float2 d;

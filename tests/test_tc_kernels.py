@@ -190,8 +190,9 @@ def test_model_rollout_tf32_vs_oracle(kind):
 
 
 def test_split_edge_kernel_v2_matches_v1_and_oracle():
-    """The split-first-Linear edge kernel (tc2.cu; forced with NLAM_TC_EDGE=v2 in a fresh process,
-    the selection is read once per process) against the fp64 oracle and the K=192 kernel."""
+    """The split-first-Linear edge kernels (tc5.cu and its predecessor tc2.cu; forced with NLAM_TC_EDGE=v2
+    [+ NLAM_TC_NO_EDGE3=1] in a fresh process, the selection is read once per process) against the fp64
+    oracle and the K=192 kernel."""
     import os
     import subprocess
     import sys
@@ -224,14 +225,16 @@ for upd, aggr in ((True, "sum"), (False, "mean")):
 print("LAUNCHES", nlb._lib.lib().nlam_launch_count())
 '''
     outs = {}
-    for mode in ("v1", "v2"):
-        env = dict(os.environ, NLAM_TC_EDGE=mode)
+    for mode, extra in (("v1", {}), ("v2", {}), ("v2", {"NLAM_TC_NO_EDGE3": "1"})):
+        env = dict(os.environ, NLAM_TC_EDGE=mode, **extra)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
-        outs[mode] = int([l for l in r.stdout.splitlines() if l.startswith("LAUNCHES")][0].split()[1])
-    # v2 issues two extra node-projection launches per InteractionNet call
-    assert outs["v2"] == outs["v1"] + 2 * 2
+        outs[mode + ("_tc2" if extra else "")] = int([l for l in r.stdout.splitlines() if l.startswith("LAUNCHES")][0].split()[1])
+    # the split formulations (tc5.cu by default, tc2.cu with NLAM_TC_NO_EDGE3=1) issue one extra launch per
+    # InteractionNet call: both node projections in a single grid
+    assert outs["v2"] == outs["v1"] + 2
+    assert outs["v2_tc2"] == outs["v2"]
 
 
 def _ell_graph(ns, nr, d, seed):
