@@ -18,6 +18,7 @@
  *                               from gnn_layers.py:188; also the backward of the gathers
  *   nlam_gather_rows         <- x.index_select(-2, edge_index[k]) in PyG propagate
  *   nlam_step_epilogue       <- rescale + residual + boundary mix
+ *   nlam_rowmlp_step_fwd     <- output_map MLP + that epilogue in one launch
  *                               (graph/base.py:339-342, forecasters/autoregressive.py:128-131)
  *
  * Conventions
@@ -155,6 +156,17 @@ int nlam_gather_rows(const float* x, int64_t x_bstride, const int32_t* idx, int6
 int nlam_step_epilogue(const float* net_out, const float* prev, const float* boundary,
                        const float* bmask, const float* diff_std, const float* diff_mean,
                        float* new_state, int64_t B, int64_t G, int64_t D, void* stream);
+
+/* output_map + step epilogue in one launch (reference graph/base.py:322-342 followed by
+ * forecasters/autoregressive.py:128-131):
+ *   y = MLP(concat_s src_s[b, r, :])                      (narrow output D < 64, no LayerNorm)
+ *   new_state = bmask * boundary + (1-bmask) * (prev + (y*diff_std + diff_mean))
+ * Tensor-core (TF32) path only: returns NLAM_E_UNSUPPORTED for other shapes / NLAM_MATH_FP32, in which case the
+ * caller issues nlam_rowmlp_fwd + nlam_step_epilogue. */
+int nlam_rowmlp_step_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const float* prev,
+                         const float* boundary, const float* bmask, const float* diff_std,
+                         const float* diff_mean, float* new_state, int64_t n_rows, int B, int flags,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ AGGR_MEAN = 0x1
 PROPAGATION = 0x2
 MATH_TF32 = 0x10
 MATH_FP32 = 0x20
+E_UNSUPPORTED = 2  # NLAM_E_UNSUPPORTED
 
 c_float_p = ctypes.c_void_p  # device pointers travel as integers
 c_int32_p = ctypes.c_void_p
@@ -90,6 +91,10 @@ SYMBOLS = {
     "nlam_gather_rows": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nlam_rowmlp_step_fwd": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p]),
     "nlam_step_epilogue": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),

@@ -18,6 +18,20 @@ extern "C" int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n
   return rowmlp_simt(mlp, srcs, n_src, res, res2, out, out2, n_rows, B, st);
 }
 
+extern "C" int nlam_rowmlp_step_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const float* prev,
+                                    const float* boundary, const float* bmask, const float* diff_std,
+                                    const float* diff_mean, float* new_state, int64_t n_rows, int B, int flags,
+                                    void* stream) {
+  NLAM_REQUIRE(mlp && srcs && prev && diff_std && diff_mean && new_state, NLAM_E_INVALID, "nlam_rowmlp_step_fwd: null argument");
+  NLAM_REQUIRE((boundary == nullptr) || bmask, NLAM_E_INVALID, "nlam_rowmlp_step_fwd: boundary without mask");
+  const int nout = mlp->out_dim[mlp->n_linear - 1];
+  // only the tensor-core path fuses the epilogue; callers fall back to nlam_rowmlp_fwd + nlam_step_epilogue
+  NLAM_REQUIRE(want_tf32(flags) && nout < 64 && !mlp->ln_gamma && tc_rowmlp_supported(mlp, srcs, n_src, nullptr, nullptr, n_rows),
+               NLAM_E_UNSUPPORTED, "nlam_rowmlp_step_fwd: shape / math mode not covered by the fused kernel");
+  StepEpilogue ep = {prev, boundary, bmask, diff_std, diff_mean};
+  return tc_rowmlp(mlp, srcs, n_src, nullptr, new_state, n_rows, B, (cudaStream_t)stream, &ep);
+}
+
 extern "C" size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, int flags) {
   (void)flags;
   if (!g) return 0;

@@ -107,8 +107,15 @@ int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
 // tc.cu
 bool tc_rowmlp_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
                          const NlamRowSrc* res2, int64_t n_rows);
+struct StepEpilogue {  // fused forecast-step epilogue of a narrow-output row MLP (see TcParams::ep_*)
+  const float* prev;
+  const float* boundary;
+  const float* mask;
+  const float* std;
+  const float* mean;
+};
 int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
-              float* out, int64_t n_rows, int B, cudaStream_t stream);
+              float* out, int64_t n_rows, int B, cudaStream_t stream, const StepEpilogue* ep = nullptr);
 bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags);
 int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs,
             const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out,

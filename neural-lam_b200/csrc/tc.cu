@@ -73,6 +73,7 @@ struct TcParams {
   long long ebs[NLAM_MAX_SRC];
   int edim[NLAM_MAX_SRC];
   int k_real;
+  int elem_bulk;  // narrow sources are staged by 1-D bulk copies (alignment checked by the host)
   const float* b1;
   const float* b2;
   const float* gamma;
@@ -92,6 +93,13 @@ struct TcParams {
   const int4* tile_meta;   // {first edge, #edges, first receiver, #receivers} per tile
   const int32_t* rowptr;
   long long n_rec;
+  // optional fused forecast-step epilogue on a narrow output (output_map): instead of the MLP output y the kernel
+  // stores  m*boundary + (1-m)*(prev + (y*std + mean))  (graph/base.py:339-342, forecasters/autoregressive.py:128-131)
+  const float* ep_prev;   // (B, n_rows, nout); NULL = no epilogue
+  const float* ep_bnd;    // (B, n_rows, nout) or NULL
+  const float* ep_mask;   // (n_rows) when ep_bnd
+  const float* ep_std;    // (nout)
+  const float* ep_mean;   // (nout)
   long long* dbg;  // optional per-phase clock64 timeline of block 0 (bring-up / profiling aid)
 };
 
@@ -130,6 +138,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   // b1 | b2 (zero past nout) | gamma | beta: there is no L1 next to 227 KB of shared memory, so a per-tile __ldg
   // of these constants would put an L2 round trip into every epilogue
   float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 1024);
+  const uint32_t bar_st_full = mb + 896;  // [2] narrow-source staging filled by bulk copies
+  const uint32_t bar_st_free = mb + 912;  // [2] ... and repacked (128 arrivals)
 
   if ((sbase & 1023u) != 0) {
     if (tid == 0) printf("nlam tc kernel: dynamic shared memory not 1024-byte aligned\n");
@@ -148,6 +158,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       mbar_init(bar_a_g4_full + 8, 1);
       mbar_init(bar_a_g4_free, 1);
       mbar_init(bar_a_g4_free + 8, 1);
+      for (int st = 0; st < 2; ++st) {
+        mbar_init(bar_st_full + 8 * st, 1);
+        mbar_init(bar_st_free + 8 * st, PROD_THREADS);
+      }
       for (int st = 0; st < 2; ++st) {
         mbar_init(bar_a_tma_full + 8 * st, 1);
         mbar_init(bar_epi_done + 8 * st, 1);
@@ -177,8 +191,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   if (tid < 64) {
     sprm[tid] = p.b1[tid];
     sprm[64 + tid] = (tid < p.nout) ? p.b2[tid] : 0.f;
-    sprm[128 + tid] = p.gamma ? p.gamma[tid] : 1.f;
-    sprm[192 + tid] = p.gamma ? p.beta[tid] : 0.f;
+    sprm[128 + tid] = p.gamma ? p.gamma[tid] : (p.ep_prev && tid < p.nout ? p.ep_std[tid] : 1.f);
+    sprm[192 + tid] = p.gamma ? p.beta[tid] : (p.ep_prev && tid < p.nout ? p.ep_mean[tid] : 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -196,6 +210,28 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       mbar_expect_tx(bar_w, (uint32_t)p.nb1 * W_BLOCK + 2u * w2_block_bytes);
       for (int j = 0; j < p.nb1; ++j) tma_load_2d(sbase + OFF_W1 + j * W_BLOCK, &tmW1, bar_w, 32 * j, 0);
       for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * W_BLOCK, &tmW2, bar_w, 32 * j, 0);
+      if (p.elem_bulk) {
+        // narrow sources (e.g. prev | prev_prev | forcing | static): the 128-row slab of every source is contiguous
+        // in global memory -> one 1-D bulk copy each into a flat staging area (A blocks 2-4 / 5-7, unused in this
+        // mode), a tile ahead of the producers that repack it into the K-major operand tile
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+          const int b = w / p.n_tiles;
+          const int t = w - b * p.n_tiles;
+          const int st = it & 1;
+          const int nrows = (int)min((long long)BM, p.n_rows - (long long)t * BM);
+          mbar_wait(bar_st_free + 8 * st, (uint32_t)(((it >> 1) & 1) ^ 1));
+          NLAM_DBG(0, it);
+          mbar_expect_tx(bar_st_full + 8 * st, (uint32_t)(nrows * p.k_real * 4));
+          uint32_t dst = sbase + OFF_A + (2 + 3 * st) * A_BLOCK;
+          for (int sidx = 0; sidx < p.n_elem; ++sidx) {
+            const int d = p.edim[sidx];
+            const float* src = p.esrc[sidx] + (long long)b * p.ebs[sidx] + (long long)t * BM * d;
+            bulk_load_1d(dst, src, (uint32_t)(nrows * d * 4), bar_st_full + 8 * st);
+            dst += (uint32_t)(BM * d * 4);
+          }
+        }
+      }
       if (has_tma_a) {
         const uint64_t pol_stream = policy_evict_first();
         int it = 0;
@@ -441,7 +477,26 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           // features, graph/base.py:275-283): producer thread pt owns tile row pt and walks its row
           // of every source; the zero padding up to nb1*32 columns was written once before the loop
           const long long gr = (long long)t * BM + pt;
-          if (gr < p.n_rows) {
+          if (p.elem_bulk) {
+            const int st = it & 1;
+            group_wait(warp == W_PROD, bar_st_full + 8 * st, (uint32_t)((it >> 1) & 1), 8, PROD_THREADS);
+            const float* stg = reinterpret_cast<const float*>(smem + OFF_A + (2 + 3 * st) * A_BLOCK);
+            int col = 0;
+#pragma unroll
+            for (int sidx = 0; sidx < NLAM_MAX_SRC; ++sidx) {
+              if (sidx < p.n_elem) {
+                const int d = p.edim[sidx];
+                const float* srow = stg + pt * d;  // lane stride d floats: conflict-free for odd d
+                for (int c = 0; c < d; ++c) {
+                  const int cc = col + c;
+                  *reinterpret_cast<float*>(smem + OFF_A + (cc >> 5) * A_BLOCK + swz(pt, (cc & 31) >> 2) + (cc & 3) * 4) = srow[c];
+                }
+                col += d;
+                stg += BM * d;
+              }
+            }
+            mbar_arrive(bar_st_free + 8 * st);
+          } else if (gr < p.n_rows) {
             int col = 0;
 #pragma unroll
             for (int sidx = 0; sidx < NLAM_MAX_SRC; ++sidx) {
@@ -675,7 +730,20 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           const float* flat = reinterpret_cast<const float*>(smem + OFF_HB);
           float* og = p.out + ((long long)b * p.n_rows + row0) * p.nout;
           const int n = nrows * p.nout;
-          for (int i = tid; i < n; i += EPI_THREADS) og[i] = flat[i];
+          if (!p.ep_prev) {
+            for (int i = tid; i < n; i += EPI_THREADS) og[i] = flat[i];
+          } else {
+            const long long g0 = ((long long)b * p.n_rows + row0) * p.nout;
+            for (int i = tid; i < n; i += EPI_THREADS) {
+              const int r = i / p.nout, c = i - r * p.nout;
+              float v1 = __ldg(p.ep_prev + g0 + i) + (flat[i] * sprm[128 + c] + sprm[192 + c]);
+              if (p.ep_bnd) {
+                const float m = __ldg(p.ep_mask + row0 + r);
+                v1 = m * __ldg(p.ep_bnd + g0 + i) + (1.0f - m) * v1;
+              }
+              og[i] = v1;
+            }
+          }
         }
       }
       if (tid == 0) NLAM_DBG(11, it);
@@ -798,12 +866,12 @@ bool tc_rowmlp_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, 
 }
 
 int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
-              int B, cudaStream_t st) {
+              int B, cudaStream_t st, const StepEpilogue* ep) {
   int nout = 0;
   NLAM_REQUIRE(mlp_shape_ok(mlp, &nout), NLAM_E_UNSUPPORTED, "tc_rowmlp: unsupported MLP shape");
   NLAM_REQUIRE(aligned16(out), NLAM_E_INVALID, "tc_rowmlp: output not 16-byte aligned");
   // dense 64-wide inputs, LayerNorm output: the streaming kernel of tc4.cu
-  if (tc_rowmlp64_supported(mlp, srcs, n_src, res, n_rows)) return tc_rowmlp64(mlp, srcs, n_src, res, out, n_rows, B, st);
+  if (!ep && tc_rowmlp64_supported(mlp, srcs, n_src, res, n_rows)) return tc_rowmlp64(mlp, srcs, n_src, res, out, n_rows, B, st);
   TcParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap a0, a1, w1, w2;
@@ -833,6 +901,12 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
       p.edim[s] = srcs[s].dim;
     }
     p.k_real = mlp->in_dim;
+    // 1-D bulk copies need 16-byte aligned slab addresses and sizes: rows % 4 == 0 makes every (128-row or tail)
+    // slab a multiple of 16 bytes; batch strides must keep the alignment
+    bool bulk = (n_rows % 4 == 0) && !getenv("NLAM_TC_NO_BULK");
+    for (int s = 0; s < n_src; ++s)
+      bulk = bulk && aligned16(srcs[s].ptr) && ((srcs[s].bstride * 4) % 16 == 0) && ((128LL * srcs[s].dim * 4) % 16 == 0);
+    p.elem_bulk = bulk ? 1 : 0;
   }
   NLAM_REQUIRE(p.nb1 * 32 >= mlp->in_dim, NLAM_E_INVALID, "tc_rowmlp: width mismatch");
   p.n2 = nout <= 32 ? 32 : 64;
@@ -848,6 +922,15 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
   p.n_rows = n_rows;
   p.B = B;
   p.n_tiles = (int)((n_rows + BM - 1) / BM);
+  if (ep) {
+    NLAM_REQUIRE(nout < 64 && !mlp->ln_gamma && !res && ep->prev && ep->std && ep->mean && (!ep->boundary || ep->mask),
+                 NLAM_E_UNSUPPORTED, "tc_rowmlp: the fused step epilogue needs a narrow output without LayerNorm / residual");
+    p.ep_prev = ep->prev;
+    p.ep_bnd = ep->boundary;
+    p.ep_mask = ep->mask;
+    p.ep_std = ep->std;
+    p.ep_mean = ep->mean;
+  }
   CUtensorMap om;
   memset(&om, 0, sizeof(om));
   if (nout == 64) {

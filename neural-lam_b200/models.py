@@ -185,6 +185,12 @@ class BaseGraphModel(StepPredictor):
         grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)  # base.py:308-310
         mesh_rep = self.process_step(mesh_rep, st)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
+        if not torch.is_grad_enabled() and not self.output_std:
+            # output_map + rescale (base.py:339) + residual (base.py:342) in one launch where the library fuses it
+            fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, None, None, self.diff_std, self.diff_mean,
+                                    flags=self.output_map.nlam_flags)
+            if fused is not None:
+                return fused, None
         net_output = self.output_map(grid_rep)
         if self.output_std:
             pred_delta_mean, pred_std_raw = net_output.chunk(2, dim=-1)
@@ -210,6 +216,10 @@ class BaseGraphModel(StepPredictor):
         grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)
         mesh_rep = self.process_step(mesh_rep, st)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
+        fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, boundary_state, boundary_mask, self.diff_std,
+                                self.diff_mean, flags=self.output_map.nlam_flags)
+        if fused is not None:
+            return fused
         net_output = self.output_map(grid_rep)
         return ops.step_epilogue(net_output, prev_state, boundary_state, boundary_mask, self.diff_std, self.diff_mean)
 

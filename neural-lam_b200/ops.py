@@ -324,6 +324,42 @@ def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean):
     return out
 
 
+def rowmlp_step(seq, x, prev, boundary, bmask, diff_std, diff_mean, flags=0):
+    """``bmask*boundary + (1-bmask)*(prev + (seq(x)*diff_std + diff_mean))`` in ONE launch
+    (``nlam_rowmlp_step_fwd``: output_map + the forecast-step epilogue); returns None when the
+    library does not fuse this shape / math mode (the caller then runs the two kernels)."""
+    L = _lib.lib()
+    if flags & _lib.MATH_FP32:
+        return None
+    xr, B, bs = as_rows(x)
+    prev = prev.contiguous()
+    _require_cuda(xr, prev, diff_std, diff_mean, boundary, bmask)
+    mlp = mlp_struct(seq)
+    D = mlp.out_dim[mlp.n_linear - 1]
+    G = xr.shape[-2]
+    if D >= 64 or mlp.ln_gamma or prev.shape != (B, G, D):
+        return None
+    arr = (NlamRowSrc * 1)()
+    arr[0].ptr = xr.data_ptr()
+    arr[0].idx = None
+    arr[0].bstride = bs
+    arr[0].dim = xr.shape[-1]
+    if boundary is not None:
+        boundary, bmask = boundary.contiguous(), bmask.contiguous()
+        assert boundary.shape == prev.shape and bmask.numel() == G
+    out = torch.empty_like(prev)
+    with torch.cuda.device(xr.device):
+        rc = L.nlam_rowmlp_step_fwd(ctypes.byref(mlp), arr, 1, prev.data_ptr(),
+                                    boundary.data_ptr() if boundary is not None else None,
+                                    bmask.data_ptr() if boundary is not None else None,
+                                    diff_std.data_ptr(), diff_mean.data_ptr(), out.data_ptr(), G, B, flags,
+                                    _stream_ptr(xr.device))
+    if rc == _lib.E_UNSUPPORTED:
+        return None
+    _lib.check(rc)
+    return out
+
+
 class RecomputeFn(torch.autograd.Function):
     """Forward = hand-written kernels (``kernel_fn``, run without autograd); backward =
     re-evaluate the same math as a differentiable graph (``torch_fn``: custom gather /
