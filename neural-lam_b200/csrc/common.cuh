@@ -38,6 +38,13 @@ int64_t launch_count();
 
 constexpr int kTileEdges = 128;  // rows of one tensor-core edge tile (UMMA M)
 
+struct StepEpilogue {  // fused forecast-step epilogue of a narrow-output row MLP (see TcParams::ep_*)
+  const float* prev;
+  const float* boundary;
+  const float* mask;
+  const float* std;
+  const float* mean;
+};
 // tc2.cu: split-first-Linear edge kernel (v2) + node projection kernel
 bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                         const float* rec, int64_t rec_bs, int B, int64_t send_rows);
@@ -52,8 +59,9 @@ int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
              cudaStream_t stream, float* ws);
 // tc4.cu
 bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
+bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows);
 int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
-                int B, cudaStream_t stream);
+                int B, cudaStream_t stream, const StepEpilogue* ep = nullptr);
 // tc3.cu
 bool tc_ell_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                       const float* rec, int64_t rec_bs, bool has_edge_out);
@@ -100,6 +108,7 @@ struct NlamGraph {
 };
 
 namespace nlam {
+
 // simt.cu
 int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
                 const NlamRowSrc* res2, float* out, float* out2, int64_t n_rows, int B,
@@ -107,13 +116,6 @@ int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
 // tc.cu
 bool tc_rowmlp_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
                          const NlamRowSrc* res2, int64_t n_rows);
-struct StepEpilogue {  // fused forecast-step epilogue of a narrow-output row MLP (see TcParams::ep_*)
-  const float* prev;
-  const float* boundary;
-  const float* mask;
-  const float* std;
-  const float* mean;
-};
 int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
               float* out, int64_t n_rows, int B, cudaStream_t stream, const StepEpilogue* ep = nullptr);
 bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags);

@@ -12,6 +12,17 @@
 //
 // 640 threads: warps 0-7 epilogue 2, warps 8-15 epilogue 1 (thread = row x 32 columns each), warp 16 MMA issue
 // (whole warp in uniform control flow, one elected lane issues), warp 17 ring loader, warp 18 output stores.
+//
+// Two further modes of the same pipeline cover the rest of the grid side of a forecast step:
+//   * NARROW INPUTS (grid embedder: prev | prev_prev | forcing | static = 17|17|18|4 columns, reference
+//     graph/base.py:275-283): the 128-row slab of every source is contiguous in global memory, so one 1-D bulk
+//     copy each lands it in a flat staging slot (ring slots 0/1); warps 17 and 19 repack it into the K-major,
+//     128B-swizzled operand tile (ring slots 2-4) — the torch.cat is never materialised and no thread waits on a
+//     global load;
+//   * NARROW OUTPUT with the forecast-step epilogue (output_map 64 -> 64 -> 17, base.py:322-342 +
+//     forecasters/autoregressive.py:128-131): second GEMM with N = 32, no LayerNorm; epilogue 2 prefetches
+//     prev / boundary / mask for its elements BEFORE it waits for the accumulators, stages y as flat [128][17] in
+//     the operand slot and writes  m*boundary + (1-m)*(prev + y*std + mean)  with coalesced stores.
 #include "tc_ptx.cuh"
 
 namespace nlam {
@@ -19,7 +30,7 @@ namespace nlam {
 namespace r4 {
 constexpr int THREADS = 640;
 constexpr int EPI = 256;
-constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_ST = 18;
+constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_ST = 18, W_RP2 = 19;  // W_RP2: second repack warp (narrow inputs)
 constexpr int NR = 5;   // ring slots
 constexpr int NT = 3;   // TMEM stages
 constexpr uint32_t BLK = 16384;
@@ -44,6 +55,20 @@ struct Row64Params {
   long long n_rows;
   int B;
   int n_tiles;
+  // narrow-input mode
+  int in_narrow;  // number of narrow sources (0 = dense 64-wide sources through the tensor maps)
+  const float* esrc[NLAM_MAX_SRC];
+  long long ebs[NLAM_MAX_SRC];
+  int edim[NLAM_MAX_SRC];
+  int k_real;
+  // narrow-output mode
+  int out_narrow;  // 0 or the output width (< 64): no LayerNorm, no residual, plain stores
+  float* out;
+  const float* ep_prev;  // fused step epilogue (NULL: store y)
+  const float* ep_bnd;
+  const float* ep_mask;
+  const float* ep_std;
+  const float* ep_mean;
   long long* dbg;
 };
 
@@ -86,7 +111,11 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const uint32_t bar_d_free = mb + 168;    // [3] 256 arrivals
   const uint32_t bar_staged = mb + 192;    // [3] output tile written over its source slot (256 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 216);
-  float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 256);  // gamma | beta
+  const uint32_t bar_st_full = mb + 224;   // [2] narrow-input staging slot filled by the bulk copies
+  const uint32_t bar_st_free = mb + 240;   // [2] ... and repacked (64 arrivals)
+  float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 256);  // gamma | beta   (narrow output: std | mean)
+  int2* ctab = reinterpret_cast<int2*>(smem + OFF_MISC + 1024);    // narrow inputs: column cc of the operand tile =
+                                                                   // staging[ctab.x + row * ctab.y] (ctab.x < 0: zero)
   const int n_src = p.n_src;
   const int nb1 = 2 * n_src;
 
@@ -95,8 +124,12 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_init(bar_w, 1);
       mbar_init(bar_wscaled, EPI);
       for (int t = 0; t < NR; ++t) {
-        mbar_init(bar_ring_full + 8 * t, 1);
+        mbar_init(bar_ring_full + 8 * t, p.in_narrow ? 64 : 1);  // repack threads / TMA transactions
         mbar_init(bar_ring_free + 8 * t, 1);
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(bar_st_full + 8 * t, 1);
+        mbar_init(bar_st_free + 8 * t, 64);
       }
       for (int t = 0; t < NT; ++t) {
         mbar_init(bar_d1_full + 8 * t, 1);
@@ -120,9 +153,28 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  if (tid < 64 && p.in_narrow) {
+    int base = 0, col = 0, found = 0;
+    int2 e = make_int2(-1, 0);
+    for (int sidx = 0; sidx < p.in_narrow; ++sidx) {
+      const int d = p.edim[sidx];
+      if (!found && tid < col + d) {
+        e = make_int2(base + (tid - col), d);
+        found = 1;
+      }
+      col += d;
+      base += 128 * d;
+    }
+    ctab[tid] = e;
+  }
   if (tid < 64) {
-    sprm[tid] = p.gamma[tid];
-    sprm[64 + tid] = p.beta[tid];
+    if (p.out_narrow) {
+      sprm[tid] = (p.ep_prev && tid < p.out_narrow) ? p.ep_std[tid] : 1.f;
+      sprm[64 + tid] = (p.ep_prev && tid < p.out_narrow) ? p.ep_mean[tid] : 0.f;
+    } else {
+      sprm[tid] = p.gamma[tid];
+      sprm[64 + tid] = p.beta[tid];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -132,17 +184,54 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const int n_work = p.n_tiles * p.B;
   int n_my = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
+  // ring slot / phase of source s of tile ti (narrow inputs: one operand tile per tile in slots 2-4)
+  auto op_slot = [&](int ti, int s) -> int { return p.in_narrow ? 2 + ti % 3 : (ti * n_src + s) % NR; };
+  auto op_phase = [&](int ti, int s) -> uint32_t {
+    return (uint32_t)(p.in_narrow ? (ti / 3) & 1 : ((ti * n_src + s) / NR) & 1);
+  };
+  // narrow inputs: thread rt (0..63, warps 17 and 19) repacks rows rt and rt+64 of tile ti from the flat staging slot
+  // into the K-major swizzled operand tile; columns k_real..63 are zero
+  auto repack_tile = [&](int ti, int rt) {
+    const int st = ti & 1;
+    const int slot = op_slot(ti, 0);
+    if (rt == 0) {
+      mbar_wait(bar_st_full + 8 * st, (uint32_t)((ti >> 1) & 1));
+      mbar_wait(bar_ring_free + 8 * slot, op_phase(ti, 0) ^ 1u);
+    }
+    named_bar_sync(12, 64);
+    uint8_t* tile = smem + OFF_RING + slot * 2 * BLK;
+    const float* stg = reinterpret_cast<const float*>(smem + OFF_RING + st * 2 * BLK);
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = rt + 64 * rr;
+      const int rx = row & 7;
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {  // one 16-byte chunk of the operand row per store
+        float4 o;
+        float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int2 e = ctab[4 * ch + u];  // broadcast read
+          ov[u] = (e.x >= 0) ? stg[e.x + row * e.y] : 0.f;  // lane stride d floats: conflict-free for odd d
+        }
+        *reinterpret_cast<float4*>(tile + (ch >> 3) * BLK + row * 128 + (((ch & 7) ^ rx) << 4)) = o;
+      }
+    }
+    fence_proxy_async();  // generic writes -> tcgen05.mma operand reads
+    mbar_arrive(bar_ring_full + 8 * slot);
+    mbar_arrive(bar_st_free + 8 * st);
+  };
 
   if (warp == W_RING) {
     // =============================== operand ring ===============================
     if (lane == 0) {
       const uint64_t pol_stream = policy_evict_first();
       const uint64_t pol_keep = policy_evict_last();
-      mbar_expect_tx(bar_w, (uint32_t)(nb1 + 2) * WBLK);
+      mbar_expect_tx(bar_w, (uint32_t)nb1 * WBLK + (p.out_narrow ? WBLK : 2u * WBLK));  // W2 box: 32 or 64 rows
       for (int kb = 0; kb < nb1; ++kb) tma_load_2d(sbase + OFF_W1 + kb * WBLK, &tmW1, bar_w, 32 * kb, 0);
       for (int kb = 0; kb < 2; ++kb) tma_load_2d(sbase + OFF_W2 + kb * WBLK, &tmW2, bar_w, 32 * kb, 0);
       int i = 0;
-      for (int ti = 0; ti < n_my; ++ti) {
+      for (int ti = 0; !p.in_narrow && ti < n_my; ++ti) {
         const int w = blockIdx.x + ti * gridDim.x;
         const int b = w / p.n_tiles, t = w - b * p.n_tiles;
         for (int s = 0; s < n_src; ++s, ++i) {
@@ -159,14 +248,43 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
       }
     }
+    if (p.in_narrow) {
+      // ---- narrow inputs: bulk copies into the staging slots (lane 0, one tile ahead) + repack (warps 17 and 19)
+      const int rt = lane;  // this thread repacks rows rt and rt + 64 (+32 for the second warp)
+      auto issue = [&](int ti) {
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int st = ti & 1;
+        const int nrows = (int)min(128LL, p.n_rows - (long long)t * 128);
+        mbar_wait(bar_st_free + 8 * st, (uint32_t)(((ti >> 1) & 1) ^ 1));
+        mbar_expect_tx(bar_st_full + 8 * st, (uint32_t)(nrows * p.k_real * 4));
+        uint32_t dst = sbase + OFF_RING + st * 2 * BLK;
+        for (int sidx = 0; sidx < p.in_narrow; ++sidx) {
+          const int d = p.edim[sidx];
+          bulk_load_1d(dst, p.esrc[sidx] + (long long)b * p.ebs[sidx] + (long long)t * 128 * d, (uint32_t)(nrows * d * 4),
+                       bar_st_full + 8 * st);
+          dst += (uint32_t)(128 * d * 4);
+        }
+        R4_DBG(0, ti);
+      };
+      if (lane == 0 && n_my > 0) issue(0);
+      for (int ti = 0; ti < n_my; ++ti) {
+        if (lane == 0 && ti + 1 < n_my) issue(ti + 1);
+        __syncwarp();
+        repack_tile(ti, rt);
+      }
+    }
+  } else if (warp == W_RP2) {
+    if (p.in_narrow)
+      for (int ti = 0; ti < n_my; ++ti) repack_tile(ti, 32 + lane);
   } else if (warp == W_ST) {
     // =============================== output stores ===============================
-    if (lane == 0) {
+    if (lane == 0 && !p.out_narrow) {
       for (int ti = 0; ti < n_my; ++ti) {
         const int w = blockIdx.x + ti * gridDim.x;
         const int b = w / p.n_tiles, t = w - b * p.n_tiles;
         const int ts = ti % NT;
-        const int slot = (ti * n_src + p.out_src) % NR;
+        const int slot = op_slot(ti, p.out_src);
         mbar_wait(bar_staged + 8 * ts, (uint32_t)((ti / NT) & 1));
         const uint32_t src = sbase + OFF_RING + slot * 2 * BLK;
         tma_store_3d(&tmOut, src, 0, t * 128, b);
@@ -181,6 +299,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   } else if (warp == W_MMA) {
     // =============================== MMA issue (uniform control flow, one elected lane) ===============================
     const uint32_t idesc = umma_idesc_tf32(128, 64);
+    const uint32_t idesc2 = p.out_narrow ? umma_idesc_tf32(128, 32) : idesc;
     mbar_wait(bar_w, 0);
     mbar_wait(bar_wscaled, 0);
     tc_fence_after();
@@ -193,17 +312,15 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       bool progress = false;
       if (g1 < n_my && g1 <= g2 + 2) {
         const int ts = g1 % NT;
-        const int i0 = g1 * n_src;
         bool ready = mbar_test_u(bar_d_free + 8 * ts, (uint32_t)(((g1 / NT) & 1) ^ 1));
-        for (int s = 0; s < n_src && ready; ++s)
-          ready = mbar_test_u(bar_ring_full + 8 * ((i0 + s) % NR), (uint32_t)(((i0 + s) / NR) & 1));
+        for (int s = 0; s < n_src && ready; ++s) ready = mbar_test_u(bar_ring_full + 8 * op_slot(g1, s), op_phase(g1, s));
         if (ready) {
           tc_fence_after();
           if (lane == 0) R4_DBG(1, g1);
           const uint32_t dd = tmem_base + ts * 128;
           if (elect_one()) {
             for (int s = 0; s < n_src; ++s) {
-              const int slot = (i0 + s) % NR;
+              const int slot = op_slot(g1, s);
               const uint64_t a0 = desc_ring + (uint64_t)((slot * 2 * BLK) >> 4);
               const uint64_t b0 = desc_w1 + (uint64_t)((s * 2 * WBLK) >> 4);
 #pragma unroll
@@ -215,7 +332,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             }
             umma_commit(bar_d1_full + 8 * ts);
             for (int s = 0; s < n_src; ++s)
-              if (s != p.out_src) umma_commit(bar_ring_free + 8 * ((i0 + s) % NR));
+              if (s != p.out_src) umma_commit(bar_ring_free + 8 * op_slot(g1, s));
           }
           __syncwarp();
           if (lane == 0) R4_DBG(2, g1);
@@ -234,7 +351,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_tf32_ts(dd, ht + (uint32_t)(jj * 32 + kk * 8), desc_w2 + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc,
+                umma_tf32_ts(dd, ht + (uint32_t)(jj * 32 + kk * 8), desc_w2 + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc2,
                              (uint32_t)((jj | kk) != 0));
             umma_commit(bar_d2_full + 8 * ts);
           }
@@ -307,10 +424,90 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const uint32_t ln_col = tmem_base + 384 + t_lane;
     float2 b2r[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) b2r[i] = make_float2(__ldg(p.b2 + c0 + 2 * i), __ldg(p.b2 + c0 + 2 * i + 1));
+    for (int i = 0; i < 16; ++i) {
+      const int c = c0 + 2 * i;
+      const int nb = p.out_narrow ? p.out_narrow : 64;
+      b2r[i] = make_float2(c < nb ? __ldg(p.b2 + c) : 0.f, c + 1 < nb ? __ldg(p.b2 + c + 1) : 0.f);
+    }
+    // narrow output: (row, column) of this thread's first element of a tile and the step of 256 elements
+    const int nout_ = p.out_narrow ? p.out_narrow : 1;
+    const int er0 = tid / nout_, ec0 = tid - er0 * nout_, eq = EPI / nout_, em = EPI - eq * nout_;
     for (int ti = 0; ti < n_my; ++ti) {
       const int ts = ti % NT;
-      const int slot = (ti * n_src + p.out_src) % NR;
+      const int slot = op_slot(ti, p.out_src);
+      if (p.out_narrow) {
+        // ---- narrow output (+ forecast-step epilogue): out = A + S*y with A, S from prev / boundary / mask / std /
+        // mean, loaded BEFORE the wait for the accumulators so that no L2 round trip sits in the tile's critical path
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int nout = p.out_narrow;
+        const int n = (int)min(128LL, p.n_rows - (long long)t * 128) * nout;
+        const long long g0 = ((long long)b * p.n_rows + (long long)t * 128) * nout;
+        float ea[9], es[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          ea[j] = 0.f;
+          es[j] = 1.f;
+        }
+        if (p.ep_prev) {
+          // all loads first (independent, in flight together), arithmetic afterwards; element i = tid + 256*j of the
+          // tile is (row, column) = (er0, ec0) advanced j times by 256 = eq*nout + em (no divisions in the loop)
+          float pv[9], bd[9], mk[9];
+          int r = er0, c = ec0;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            const int i = tid + EPI * j;
+            const bool act = i < n;
+            pv[j] = act ? __ldg(p.ep_prev + g0 + i) : 0.f;
+            bd[j] = (act && p.ep_bnd) ? __ldg(p.ep_bnd + g0 + i) : 0.f;
+            mk[j] = (act && p.ep_bnd) ? __ldg(p.ep_mask + (long long)t * 128 + r) : 0.f;
+            c += em;
+            r += eq;
+            if (c >= nout) {
+              c -= nout;
+              ++r;
+            }
+          }
+          c = ec0;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            if (tid + EPI * j < n) {
+              ea[j] = mk[j] * bd[j] + (1.0f - mk[j]) * (pv[j] + sprm[64 + c]);
+              es[j] = (1.0f - mk[j]) * sprm[c];
+            }
+            c += em;
+            if (c >= nout) c -= nout;
+          }
+        }
+        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
+        named_bar_sync(2, EPI);
+        tc_fence_after();
+        if (tid == 0) R4_DBG(5, ti);
+        float* flat = reinterpret_cast<float*>(smem + OFF_RING + slot * 2 * BLK);  // GEMM1 has consumed the operand tile
+        if (half == 0) {
+          float vf[32];
+          tmem_ld32(tmem_base + ts * 128 + t_lane, vf);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (2 * i < nout) flat[row * nout + 2 * i] = vf[2 * i] + b2r[i].x;  // pitch nout floats: conflict-free for odd nout
+            if (2 * i + 1 < nout) flat[row * nout + 2 * i + 1] = vf[2 * i + 1] + b2r[i].y;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_d_free + 8 * ts);
+        named_bar_sync(3, EPI);  // flat tile complete
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int i = tid + EPI * j;
+          if (i < n) p.out[g0 + i] = fmaf(es[j], flat[i], ea[j]);
+        }
+        named_bar_sync(3, EPI);  // flat tile consumed: the slot may be refilled
+        if (tid == 0) {
+          mbar_arrive(bar_ring_free + 8 * slot);
+          R4_DBG(6, ti);
+        }
+        continue;
+      }
       if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
       named_bar_sync(2, EPI);
       tc_fence_after();
@@ -371,20 +568,41 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ host
-bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows) {
+static bool row64_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("NLAM_TC_ROW");
     on = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1;
   }
-  if (!on) return false;
+  return on != 0;
+}
+
+// input side: 1-2 dense 64-wide sources (TMA ring), or up to 4 narrow sources whose widths sum to in_dim <= 64 (bulk
+// copies: 16-byte aligned slabs).  Returns 0 (unsupported), 1 (dense), 2 (narrow).
+static int row64_input_kind(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows) {
+  if (n_src < 1 || n_src > NLAM_MAX_SRC) return 0;
+  bool wide = n_src <= 2 && mlp->in_dim == 64 * n_src;
+  for (int s = 0; s < n_src && wide; ++s)
+    wide = srcs[s].dim == 64 && !srcs[s].idx && aligned16(srcs[s].ptr) && srcs[s].bstride % 4 == 0;
+  if (wide) return 1;
+  if (mlp->in_dim > 64 || n_rows % 4 != 0) return 0;
+  int k = 0;
+  for (int s = 0; s < n_src; ++s) {
+    if (srcs[s].idx || !aligned16(srcs[s].ptr) || (srcs[s].bstride * 4) % 16 != 0 || srcs[s].dim < 1) return 0;
+    k += srcs[s].dim;
+  }
+  return k == mlp->in_dim ? 2 : 0;
+}
+
+bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows) {
+  if (!row64_enabled()) return false;
   int nout = 0;
-  if (n_src < 1 || n_src > 2 || n_rows < 1 || n_rows >= (1LL << 31) - 256) return false;
-  if (!mlp_shape_ok(mlp, &nout) || nout != 64 || !mlp->ln_gamma || !mlp->ln_beta || mlp->in_dim != 64 * n_src) return false;
-  for (int s = 0; s < n_src; ++s)
-    if (srcs[s].dim != 64 || srcs[s].idx || !aligned16(srcs[s].ptr) || srcs[s].bstride % 4 != 0) return false;
+  if (n_rows < 1 || n_rows >= (1LL << 31) - 256) return false;
+  if (!mlp_shape_ok(mlp, &nout) || nout != 64 || !mlp->ln_gamma || !mlp->ln_beta) return false;
+  const int kind = row64_input_kind(mlp, srcs, n_src, n_rows);
+  if (!kind) return false;
   if (res) {
-    if (res->idx) return false;
+    if (res->idx || kind != 1) return false;
     bool match = false;
     for (int s = 0; s < n_src; ++s) match = match || (srcs[s].ptr == res->ptr && srcs[s].bstride == res->bstride);
     if (!match) return false;
@@ -392,34 +610,77 @@ bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src
   return true;
 }
 
+// narrow output (<= 18 columns, no LayerNorm, no residual), optionally with the forecast-step epilogue
+bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows) {
+  if (!row64_enabled()) return false;
+  int nout = 0;
+  if (n_rows < 1 || n_rows >= (1LL << 31) - 256) return false;
+  if (!mlp_shape_ok(mlp, &nout) || nout > 18 || mlp->ln_gamma) return false;
+  return row64_input_kind(mlp, srcs, n_src, n_rows) != 0;
+}
+
 int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
-                int B, cudaStream_t st) {
-  NLAM_REQUIRE(aligned16(out), NLAM_E_INVALID, "tc_rowmlp64: output not 16-byte aligned");
+                int B, cudaStream_t st, const StepEpilogue* ep) {
+  int nout = 0;
+  NLAM_REQUIRE(mlp_shape_ok(mlp, &nout), NLAM_E_UNSUPPORTED, "tc_rowmlp64: unsupported MLP shape");
+  const bool narrow_out = nout < 64;
+  NLAM_REQUIRE(narrow_out || aligned16(out), NLAM_E_INVALID, "tc_rowmlp64: output not 16-byte aligned");
+  NLAM_REQUIRE(!ep || narrow_out, NLAM_E_UNSUPPORTED, "tc_rowmlp64: the step epilogue needs a narrow output");
+  const int kind = row64_input_kind(mlp, srcs, n_src, n_rows);
+  NLAM_REQUIRE(kind != 0, NLAM_E_UNSUPPORTED, "tc_rowmlp64: unsupported inputs");
   Row64Params p;
   memset(&p, 0, sizeof(p));
   CUtensorMap a[2], w1, w2, om;
   memset(a, 0, sizeof(a));
-  p.n_src = n_src;
+  memset(&om, 0, sizeof(om));
   p.out_src = 0;
-  for (int s = 0; s < n_src; ++s) {
-    const bool batched = srcs[s].bstride != 0 && B > 1;
-    p.batched[s] = batched;
-    int rc = make_map(&a[s], srcs[s].ptr, 64, (uint64_t)n_rows, batched ? (uint64_t)B : 1, 64,
-                      batched ? (uint64_t)srcs[s].bstride : (uint64_t)n_rows * 64, 128, true);
-    if (rc) return rc;
+  int rc;
+  if (kind == 1) {
+    p.n_src = n_src;
+    for (int s = 0; s < n_src; ++s) {
+      const bool batched = srcs[s].bstride != 0 && B > 1;
+      p.batched[s] = batched;
+      rc = make_map(&a[s], srcs[s].ptr, 64, (uint64_t)n_rows, batched ? (uint64_t)B : 1, 64,
+                    batched ? (uint64_t)srcs[s].bstride : (uint64_t)n_rows * 64, 128, true);
+      if (rc) return rc;
+    }
+    if (n_src == 1) a[1] = a[0];
+  } else {
+    p.n_src = 1;  // one repacked operand tile per row tile
+    p.in_narrow = n_src;
+    p.k_real = mlp->in_dim;
+    for (int s = 0; s < n_src; ++s) {
+      p.esrc[s] = srcs[s].ptr;
+      p.ebs[s] = (B > 1) ? srcs[s].bstride : 0;
+      p.edim[s] = srcs[s].dim;
+    }
   }
   if (res) {
     p.has_res = 1;
     for (int s = n_src - 1; s >= 0; --s)
       if (srcs[s].ptr == res->ptr && srcs[s].bstride == res->bstride) p.out_src = s;
   }
-  if (n_src == 1) a[1] = a[0];
-  int rc = make_map(&w1, mlp->w[0], (uint64_t)mlp->in_dim, 64, 1, (uint64_t)mlp->in_dim, 0, 64, false);
+  // W1: (64, in_dim) row-major; K blocks past in_dim (narrow inputs, in_dim < 64) are zero-filled by TMA
+  rc = make_map(&w1, mlp->w[0], (uint64_t)mlp->in_dim, 64, 1, (uint64_t)mlp->in_dim, 0, 64, false);
   if (rc) return rc;
-  rc = make_map(&w2, mlp->w[1], 64, 64, 1, 64, 0, 64, false);
+  rc = make_map(&w2, mlp->w[1], 64, (uint64_t)nout, 1, 64, 0, narrow_out ? 32 : 64, false);
   if (rc) return rc;
-  rc = make_map(&om, out, 64, (uint64_t)n_rows, (uint64_t)B, 64, (uint64_t)n_rows * 64, 128, true);
-  if (rc) return rc;
+  if (kind == 2) a[0] = a[1] = w1;  // unused tensor-map slots must still be valid objects
+  if (!narrow_out) {
+    rc = make_map(&om, out, 64, (uint64_t)n_rows, (uint64_t)B, 64, (uint64_t)n_rows * 64, 128, true);
+    if (rc) return rc;
+  } else {
+    om = w1;
+    p.out_narrow = nout;
+    p.out = out;
+    if (ep) {
+      p.ep_prev = ep->prev;
+      p.ep_bnd = ep->boundary;
+      p.ep_mask = ep->mask;
+      p.ep_std = ep->std;
+      p.ep_mean = ep->mean;
+    }
+  }
   p.b1 = mlp->b[0];
   p.b2 = mlp->b[1];
   p.gamma = mlp->ln_gamma;
