@@ -424,6 +424,7 @@ constexpr int G2_THREADS = 256;
 constexpr int E1_THREADS = 256;
 constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_GA = 18;
 constexpr int NR = 3;
+constexpr int NT = 3;  // TMEM stages (D | hidden) of sub-tiles in flight
 constexpr uint32_t BLK = 16384;
 constexpr uint32_t WBLK = 8192;
 constexpr uint32_t OFF_W1E = 0;
@@ -476,12 +477,12 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
   const uint32_t bar_win_full = mb + 56;    // [2] sender window gathered
   const uint32_t bar_staged = mb + 72;      // [2] aggregate of the tile staged in its window buffer (256 arrivals)
   const uint32_t bar_dr_full = mb + 88;     // [2]
-  const uint32_t bar_d1_full = mb + 104;    // [2]
-  const uint32_t bar_hb_full = mb + 120;    // [2]
-  const uint32_t bar_d2_full = mb + 136;    // [2]
-  const uint32_t bar_d_free = mb + 152;     // [2]
-  const uint32_t bar_wscaled = mb + 168;    // first-Linear weight tiles halved in place (256 arrivals)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 176);
+  const uint32_t bar_d1_full = mb + 104;    // [3] per TMEM stage
+  const uint32_t bar_hb_full = mb + 128;    // [3]
+  const uint32_t bar_d2_full = mb + 152;    // [3]
+  const uint32_t bar_d_free = mb + 176;     // [3]
+  const uint32_t bar_wscaled = mb + 200;    // first-Linear weight tiles halved in place (256 arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 208);
   float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 256);  // b1 | b2 | gamma | beta
   const int d = p.d;
 
@@ -497,6 +498,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         mbar_init(bar_win_full + 8 * t, 1);
         mbar_init(bar_staged + 8 * t, G2_THREADS);
         mbar_init(bar_dr_full + 8 * t, 1);
+      }
+      for (int t = 0; t < NT; ++t) {
         mbar_init(bar_d1_full + 8 * t, 1);
         mbar_init(bar_hb_full + 8 * t, E1_THREADS);
         mbar_init(bar_d2_full + 8 * t, 1);
@@ -528,7 +531,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns: D_r[tile parity] at 0 / 64; sub-tile stage ts: D at 128 + ts*128, hidden +64; LN scratch 384
+  // TMEM columns: D_r[tile parity] at 0 / 64; sub-tile stage ts = j mod 3: D at 128 + ts*128, hidden +64 (512 columns
+  // in all); the LayerNorm scratch of a sub-tile lives in its own hidden columns, dead once its second GEMM is done
   const int n_work = p.n_tiles * p.B;
   int n_my = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
@@ -658,10 +662,10 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
               m = 1;
               progress = true;
             }
-          } else if (g1 <= g2 + 1) {
-            const int j = g1, ts = j & 1;
+          } else if (g1 <= g2 + NT - 1) {
+            const int j = g1, ts = j % NT;
             if (mbar_test(bar_ring_full + 8 * slot, (uint32_t)((item / NR) & 1)) &&
-                mbar_test(bar_d_free + 8 * ts, (uint32_t)(((j >> 1) & 1) ^ 1))) {
+                mbar_test(bar_d_free + 8 * ts, (uint32_t)(((j / NT) & 1) ^ 1))) {
               tc_fence_after();
               E3_DBG(8, j);
               const uint32_t dd = tmem_base + 128 + ts * 128;
@@ -682,8 +686,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
           }
         }
         if (g2 < g1) {
-          const int j = g2, ts = j & 1;
-          if (mbar_test(bar_hb_full + 8 * ts, (uint32_t)((j >> 1) & 1))) {
+          const int j = g2, ts = j % NT;
+          if (mbar_test(bar_hb_full + 8 * ts, (uint32_t)((j / NT) & 1))) {
             tc_fence_after();
             E3_DBG(9, j);
             const uint32_t dd = tmem_base + 128 + ts * 128;
@@ -745,7 +749,7 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     int loc_next = load_loc(0);
     int ti = 0, k = 0;
     for (int j = 0; j < n_sub; ++j) {
-      const int ts = j & 1;
+      const int ts = j % NT;
       const int loc = loc_next;
       loc_next = load_loc(j + 1);
       if (lead) {
@@ -753,7 +757,7 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
           mbar_wait(bar_dr_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
           mbar_wait(bar_win_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
         }
-        mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((j >> 1) & 1));
+        mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((j / NT) & 1));
       }
       named_bar_sync(1, E1_THREADS);
       tc_fence_after();
@@ -798,7 +802,6 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     const int c0 = half * 32;
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
     const int pbar = 4 + q;
-    const uint32_t ln_col = tmem_base + 384 + t_lane;
     // aggregate = gamma * sum_k (v_k - mu_k) * rstd_k + d * beta: accumulate sum_k v_k*rstd_k per column and
     // sum_k mu_k*rstd_k per row; gamma / beta are applied once per tile
     float2 acc[16];
@@ -808,16 +811,15 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     int j = 0;
     for (int ti = 0; ti < n_my; ++ti) {
       for (int k = 0; k < d; ++k, ++j) {
-        const int ts = j & 1;
-        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((j >> 1) & 1));
+        const int ts = j % NT;
+        const uint32_t ln_col = tmem_base + 128 + ts * 128 + 64 + t_lane;  // scratch in the stage's dead hidden columns
+        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((j / NT) & 1));
         if (tid == 0) E3_DBG(5, j);
         named_bar_sync(2, G2_THREADS);
         tc_fence_after();
         if (tid == 0) E3_DBG(6, j);
         float vf[32];
         tmem_ld32(tmem_base + 128 + ts * 128 + t_lane + c0, vf);
-        tc_fence_before();
-        mbar_arrive(bar_d_free + 8 * ts);
         float2 v[16];
         float2 sm2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -837,6 +839,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         tc_fence_after();
         float st4[4];
         tmem_ld4(ln_col, st4);
+        tc_fence_before();
+        mbar_arrive(bar_d_free + 8 * ts);  // accumulators and the scratch (hidden columns) of this stage are free again
         const float mu = (st4[0] + st4[2]) * (1.0f / 64.0f);
         const float ex2 = (st4[1] + st4[3]) * (1.0f / 64.0f);
         const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);

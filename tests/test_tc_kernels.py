@@ -113,6 +113,16 @@ ROW_CASES = [
     ("output_map_17", [64, 64, 17], [(2, 500, 64)], None, False),
     ("grid_embedder_56", [56, 64, 64], [(2, 400, 17), (2, 400, 17), (2, 400, 18), (400, 4)], None, True),
     ("one_row", [64, 64, 64], [(1, 1, 64)], None, True),
+    # streaming kernel (tc4.cu), several tiles per CTA, partial last tile
+    ("enc_many_tiles", [64, 64, 64], [(2, 128 * 300 + 77, 64)], 0, True),
+    ("node_many_tiles", [128, 64, 64], [(2, 128 * 200 + 3, 64), (2, 128 * 200 + 3, 64)], 0, True),
+    ("node_res_aggr_many", [128, 64, 64], [(2, 128 * 160 + 9, 64), (2, 128 * 160 + 9, 64)], 1, True),
+    # narrow inputs staged by bulk copies + repack (rows % 4 == 0; otherwise the element-wise loader), narrow output
+    ("embedder_many_tiles", [56, 64, 64], [(2, 128 * 200 + 8, 17), (2, 128 * 200 + 8, 17), (2, 128 * 200 + 8, 18),
+                                           (128 * 200 + 8, 4)], None, True),
+    ("embedder_rows_not_mult4", [56, 64, 64], [(2, 401, 17), (2, 401, 17), (2, 401, 18), (401, 4)], None, True),
+    ("output_map_many_tiles", [64, 64, 17], [(3, 128 * 200 + 5, 64)], None, False),
+    ("narrow_in_narrow_out", [20, 64, 9], [(2, 1000, 13), (2, 1000, 7)], None, False),
 ]
 
 
@@ -296,3 +306,34 @@ def test_uniform_degree_edge_kernels_vs_oracle(case):
     err = (got.double().cpu() - want[0]).abs().max().item()
     assert err <= ABS_TOL, (name, err)
     assert err <= max(3 * ref_err, 4e-3), (name, err, ref_err)
+
+
+@pytest.mark.parametrize("with_boundary", [False, True])
+def test_fused_output_map_step_epilogue(with_boundary):
+    """nlam_rowmlp_step_fwd: output_map + rescale + residual (+ boundary mix) in one launch (reference
+    graph/base.py:322-342, forecasters/autoregressive.py:128-131) against the fp64 formula on the oracle MLP."""
+    torch.manual_seed(0)
+    B, G, D = 3, 128 * 40 + 12, 17
+    m = nlb.make_mlp([64, 64, D], layer_norm=False)
+    x, prev, bnd = torch.randn(B, G, 64), torch.randn(B, G, D), torch.randn(B, G, D)
+    mask = (torch.rand(G) < 0.3).float()
+    std, mean = torch.rand(D) + 0.5, torch.randn(D)
+    y = rp.mlp(x.double(), {f"m.{k}": v.double() for k, v in m.state_dict().items()}, "m", layer_norm=False)
+    want = prev.double() + (y * std.double() + mean.double())
+    if with_boundary:
+        mk = mask.double()[None, :, None]
+        want = mk * bnd.double() + (1 - mk) * want
+    m = m.to(DEV)
+    n0 = _lib.lib().nlam_launch_count()
+    with torch.no_grad():
+        got = ops.rowmlp_step(m, x.to(DEV), prev.to(DEV), bnd.to(DEV) if with_boundary else None,
+                              mask.to(DEV) if with_boundary else None, std.to(DEV), mean.to(DEV))
+    assert got is not None, "the TF32 path must fuse this shape"
+    assert _lib.lib().nlam_launch_count() == n0 + 1
+    err = (got.double().cpu() - want).abs().max().item()
+    assert err <= ABS_TOL, err
+    if with_boundary:  # boundary nodes are copied exactly
+        sel = mask.bool()
+        assert torch.equal(got.cpu()[:, sel], bnd[:, sel])
+    # the exact-fp32 mode does not fuse: callers fall back to the two kernels
+    assert ops.rowmlp_step(m, x.to(DEV), prev.to(DEV), None, None, std.to(DEV), mean.to(DEV), flags=_lib.MATH_FP32) is None
