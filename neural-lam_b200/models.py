@@ -204,9 +204,9 @@ class BaseGraphModel(StepPredictor):
         return self.get_clamped_new_state(rescaled, prev_state), pred_std
 
     @torch.no_grad()
-    def forward_with_boundary(self, prev_state, prev_prev_state, forcing, boundary_state, boundary_mask):
+    def forward_with_boundary(self, prev_state, prev_prev_state, forcing, boundary_state, boundary_mask, out=None):
         """Inference step with the ARForecaster boundary mix (autoregressive.py:128-131) fused
-        into the step epilogue kernel."""
+        into the step epilogue kernel.  ``out``: optional preallocated (B,G,d) tensor for the new state."""
         assert not self.output_std
         B = prev_state.shape[0]
         grid_emb = self.grid_embedder.apply_rows(
@@ -217,11 +217,12 @@ class BaseGraphModel(StepPredictor):
         mesh_rep = self.process_step(mesh_rep, st)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
         fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, boundary_state, boundary_mask, self.diff_std,
-                                self.diff_mean, flags=self.output_map.nlam_flags)
+                                self.diff_mean, flags=self.output_map.nlam_flags, out=out)
         if fused is not None:
             return fused
         net_output = self.output_map(grid_rep)
-        return ops.step_epilogue(net_output, prev_state, boundary_state, boundary_mask, self.diff_std, self.diff_mean)
+        return ops.step_epilogue(net_output, prev_state, boundary_state, boundary_mask, self.diff_std, self.diff_mean,
+                                 out=out)
 
 
 class GraphLAM(BaseGraphModel):
@@ -426,49 +427,68 @@ class ARForecaster(nn.Module):
     # ---- inference fast path: one captured CUDA graph per (B, shapes) ----------------------
     @torch.no_grad()
     def capture(self, batch_size):
-        """Capture one forecast step (predictor + boundary mix) into a CUDA graph operating on
-        static buffers.  Returns the dict of static buffers."""
+        """Capture the forecast step (predictor + boundary mix) into CUDA graphs operating on static buffers.
+        The states live in a ring of three buffers — step k reads prev_prev = state[k%3], prev = state[(k+1)%3] and
+        writes the new state into state[(k+2)%3] — so the autoregressive feedback costs no copies; the three
+        rotations are three graphs sharing one memory pool.  Returns the dict of static buffers
+        (``forcing``, ``boundary``, ``state``)."""
         p = self.predictor
         dev = self.boundary_mask.device
         G, d, f = p.num_grid_nodes, p.num_state_vars, p.grid_input_dim - 2 * p.num_state_vars - p.grid_static_features.shape[1]
-        bufs = {k: torch.zeros(batch_size, G, w, device=dev) for k, w in
-                (("prev", d), ("prev_prev", d), ("forcing", f), ("boundary", d))}
+        bufs = {"forcing": torch.zeros(batch_size, G, f, device=dev), "boundary": torch.zeros(batch_size, G, d, device=dev),
+                "state": [torch.zeros(batch_size, G, d, device=dev) for _ in range(3)]}
         p.static_embeddings()  # materialise the weight-only embeddings outside the graph
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):  # warm up allocator / lazy handles
-                out = self._one_step(bufs)
+                self._one_step(bufs, 0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = self._one_step(bufs)
-        bufs["out"] = out
-        self._graph = (batch_size, graph, bufs)
+        graphs = []
+        for k in range(3):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=graphs[0].pool() if graphs else None):
+                self._one_step(bufs, k)
+            graphs.append(g)
+        self._graph = (batch_size, graphs, bufs)
+        self._phase = 0
         return bufs
 
-    def _one_step(self, bufs):
-        return self.predictor.forward_with_boundary(bufs["prev"], bufs["prev_prev"], bufs["forcing"],
-                                                    bufs["boundary"], self.boundary_mask)
+    def _one_step(self, bufs, k):
+        st = bufs["state"]
+        return self.predictor.forward_with_boundary(st[(k + 1) % 3], st[k % 3], bufs["forcing"], bufs["boundary"],
+                                                    self.boundary_mask, out=st[(k + 2) % 3])
+
+    def set_state(self, prev_prev_state, prev_state):
+        """Load the two initial states into the captured step's state ring."""
+        _, _, bufs = self._graph
+        bufs["state"][0].copy_(prev_prev_state)
+        bufs["state"][1].copy_(prev_state)
+        self._phase = 0
+
+    def replay_step(self):
+        """Replay one captured forecast step on the static ``forcing`` / ``boundary`` buffers; returns the buffer
+        holding the new state (valid until two further steps have been replayed)."""
+        _, graphs, bufs = self._graph
+        k = self._phase
+        graphs[k].replay()
+        self._phase = (k + 1) % 3
+        return bufs["state"][(k + 2) % 3]
 
     @torch.no_grad()
     def rollout_graphed(self, init_states, forcing_features, boundary_states):
-        """Same result as ``forward`` (no std), replaying the captured step graph."""
+        """Same result as ``forward`` (no std), replaying the captured step graphs."""
         B, T = forcing_features.shape[0], forcing_features.shape[1]
         if self._graph is None or self._graph[0] != B:
             self.capture(B)
-        _, graph, bufs = self._graph
+        _, _, bufs = self._graph
         out = torch.empty(B, T, *init_states.shape[2:], device=init_states.device)
-        bufs["prev_prev"].copy_(init_states[:, 0])
-        bufs["prev"].copy_(init_states[:, 1])
+        self.set_state(init_states[:, 0], init_states[:, 1])
         for i in range(T):
             bufs["forcing"].copy_(forcing_features[:, i])
             bufs["boundary"].copy_(boundary_states[:, i])
-            graph.replay()
-            out[:, i].copy_(bufs["out"])
-            bufs["prev_prev"].copy_(bufs["prev"])
-            bufs["prev"].copy_(bufs["out"])
+            out[:, i].copy_(self.replay_step())
         return out
 
     @torch.no_grad()
@@ -483,7 +503,7 @@ class ARForecaster(nn.Module):
         dev = self.boundary_mask.device
         if self._graph is None or self._graph[0] != B:
             self.capture(B)
-        _, graph, bufs = self._graph
+        _, _, bufs = self._graph
         if out is None:
             out = torch.empty(B, T, *init_states.shape[2:], dtype=torch.float32, pin_memory=True)
         if getattr(self, "_io", None) is None or self._io["B"] != B:
@@ -491,7 +511,7 @@ class ARForecaster(nn.Module):
                 "B": B, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
                 "forc": [torch.empty_like(bufs["forcing"]) for _ in range(2)],
                 "bnd": [torch.empty_like(bufs["boundary"]) for _ in range(2)],
-                "out": [torch.empty_like(bufs["out"]) for _ in range(2)],
+                "out": [torch.empty_like(bufs["boundary"]) for _ in range(2)],
             }
         io = self._io
         main = torch.cuda.current_stream(dev)
@@ -514,8 +534,9 @@ class ARForecaster(nn.Module):
                 in_ready[k].record(s_in)
 
         for b in range(B):
-            bufs["prev_prev"][b].copy_(init_states[b, 0], non_blocking=True)
-            bufs["prev"][b].copy_(init_states[b, 1], non_blocking=True)
+            bufs["state"][0][b].copy_(init_states[b, 0], non_blocking=True)
+            bufs["state"][1][b].copy_(init_states[b, 1], non_blocking=True)
+        self._phase = 0
         h2d(0)
         for i in range(T):
             k = i & 1
@@ -525,18 +546,16 @@ class ARForecaster(nn.Module):
             bufs["forcing"].copy_(io["forc"][k])
             bufs["boundary"].copy_(io["bnd"][k])
             in_free[k].record(main)
-            graph.replay()
+            new_state = self.replay_step()
             if i >= 2:
                 main.wait_event(out_free[k])
-            io["out"][k].copy_(bufs["out"])
+            io["out"][k].copy_(new_state)
             out_ready[k].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(out_ready[k])
                 for b in range(B):
                     out[b, i].copy_(io["out"][k][b], non_blocking=True)
                 out_free[k].record(s_out)
-            bufs["prev_prev"].copy_(bufs["prev"])
-            bufs["prev"].copy_(bufs["out"])
         main.wait_stream(s_out)
         main.wait_stream(s_in)
         main.synchronize()

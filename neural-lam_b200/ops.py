@@ -305,13 +305,15 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     return rec_out, edge_out, aggr
 
 
-def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean):
+def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None):
     """new = bmask*boundary + (1-bmask)*(prev + net_out*diff_std + diff_mean) (no-grad path)."""
     L = _lib.lib()
     net_out, prev = net_out.contiguous(), prev.contiguous()
     _require_cuda(net_out, prev, diff_std, diff_mean, boundary, bmask)
     B, G, D = net_out.shape
-    out = torch.empty_like(net_out)
+    if out is None:
+        out = torch.empty_like(net_out)
+    assert out.is_contiguous() and out.shape == net_out.shape
     if boundary is not None:
         boundary, bmask = boundary.contiguous(), bmask.contiguous()
         assert bmask.numel() == G
@@ -324,7 +326,7 @@ def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean):
     return out
 
 
-def rowmlp_step(seq, x, prev, boundary, bmask, diff_std, diff_mean, flags=0):
+def rowmlp_step(seq, x, prev, boundary, bmask, diff_std, diff_mean, flags=0, out=None):
     """``bmask*boundary + (1-bmask)*(prev + (seq(x)*diff_std + diff_mean))`` in ONE launch
     (``nlam_rowmlp_step_fwd``: output_map + the forecast-step epilogue); returns None when the
     library does not fuse this shape / math mode (the caller then runs the two kernels)."""
@@ -347,7 +349,9 @@ def rowmlp_step(seq, x, prev, boundary, bmask, diff_std, diff_mean, flags=0):
     if boundary is not None:
         boundary, bmask = boundary.contiguous(), bmask.contiguous()
         assert boundary.shape == prev.shape and bmask.numel() == G
-    out = torch.empty_like(prev)
+    if out is None:
+        out = torch.empty_like(prev)
+    assert out.is_contiguous() and out.shape == prev.shape and out.data_ptr() != prev.data_ptr()
     with torch.cuda.device(xr.device):
         rc = L.nlam_rowmlp_step_fwd(ctypes.byref(mlp), arr, 1, prev.data_ptr(),
                                     boundary.data_ptr() if boundary is not None else None,
