@@ -1,26 +1,26 @@
-// Edge kernel v2 for H = 64 ("split first Linear") + the node projection kernel that feeds it.
+// Node projection kernel of the split first Linear + the FIRST split edge kernel (kept as a fallback).
 //
 // The first Linear of the edge MLP acts on [e | x_src | x_dst] (reference gnn_layers.py:168-172).  It is
 // linear, so   W1·[e; x_s; x_r] + b1 = W1e·e + (W1s·x)_src + (W1r·x + b1)_dst .
 // The two node-side terms are computed once per NODE by `tc_rowlinear_kernel` (P_s = x_send·W1sᵀ,
-// P_r = x_rec·W1rᵀ + b1) instead of once per EDGE, and the edge kernel only runs the K=64 GEMM
-// e·W1eᵀ on the tensor cores and adds the gathered projections in its first epilogue.  Compared with
-// the K=192 formulation (tc.cu) this removes 2/3 of the first GEMM and of its shared-memory operand
-// traffic, halves the gathered bytes (receiver rows repeat along a CSR segment: their loads coalesce
-// to one request per distinct receiver), and shrinks the per-tile shared-memory footprint to 64 KB,
-// which buys THREE tiles in flight and two independent second-epilogue warp groups.
-// Summation order differs from the reference (three TF32 GEMMs summed in fp32) — inside the stated
-// TF32 tolerance.
+// P_r = x_rec·W1rᵀ + b1; both problems of a call in ONE launch) instead of once per EDGE, and the edge kernel only
+// runs the K=64 GEMM e·W1eᵀ on the tensor cores and adds the gathered projections in its first epilogue.
+// Summation order differs from the reference (three TF32 GEMMs summed in fp32) — inside the stated TF32 tolerance.
+//
+// The edge kernel in use is tc_edge3_kernel (tc5.cu); `tc_edge2_kernel` below is its predecessor (896 threads at
+// 72 registers — it spills —, two alternating groups per epilogue, segmented sum inside epilogue 2), reachable
+// with NLAM_TC_NO_EDGE3=1 and covered by tests/test_tc_kernels.py.  It shares the sender windows of the graph
+// handle (one tile::gather4 per 4 DISTINCT sender rows of a tile) and the packed-fp32 epilogue arithmetic.
 //
 // tc_edge2_kernel: 896 threads, 1 CTA/SM, persistent over (batch, tile):
 //   warps 0-7   epilogue-2 group 0 (tiles 0,2,4,..)   } D2 -> bias, LayerNorm, messages staged in the
-//   warps 8-15  epilogue-2 group 1 (tiles 1,3,5,..)   } tile's P_s buffer, e' = e + m in place + TMA
+//   warps 8-15  epilogue-2 group 1 (tiles 1,3,5,..)   } tile's window buffer, e' = e + m in place + TMA
 //                                                       store, CSR segmented sum -> aggr
-//   warps 16-23 epilogue-1, two groups alternating tiles: D1 + P_s[src] (smem) + P_r[dst] (global) ->
+//   warps 16-23 epilogue-1, two groups alternating tiles: D1 + P_s[window row] (smem) + P_r[dst] (global) ->
 //               SiLU -> hidden in TMEM
 //   warp 24     tcgen05.mma issue (GEMM1 SS form K=64, GEMM2 TS form, A = hidden in TMEM)
-//   warps 25-27 loaders: weights once; per tile the e tile (TMA) + 64 tile::gather4 (4 rows x 128 B) of P_s
-// Shared memory: W1e 16 KB | W2 16 KB | 3 stages x (e 32 KB + P_s 32 KB) | misc = 227 KB.
+//   warps 25-27 loaders: weights once; per tile the e tile (TMA) + the window's gather4 operations
+// Shared memory: W1e 16 KB | W2 16 KB | 3 stages x (e 32 KB + window 32 KB) | misc = 227 KB.
 // TMEM: 2 stages x (D 64 cols [D1, later D2] + hidden 64 cols) + LayerNorm scratch.
 #include "tc_ptx.cuh"
 
