@@ -68,3 +68,22 @@ def test_index_tables(seed):
     for s in range(net.num_send_min):
         assert np.all(snd[so[sp[s]:sp[s + 1]]] == s)
     assert net.max_in_degree == np.bincount(rcv).max()
+
+
+def test_synthetic_graph_degrees_match_the_kernel_selection():
+    """The receiver-tiled (ELL) kernels are selected for edge sets with a uniform in-degree: mesh->grid gives every
+    grid node exactly its 4 nearest mesh nodes (reference create_graph.py:779-792), hierarchical down edges give every
+    node one parent; grid->mesh and the mesh graph itself have varying in-degrees (general CSR kernels)."""
+    import torch
+    from neural_lam_b200 import synthetic
+
+    spec = synthetic.make_graph_spec(30, 27)
+    G = 30 * 27
+    deg = torch.bincount(spec["m2g_edge_index"][1], minlength=G)
+    assert deg.min().item() == deg.max().item() == 4
+    assert torch.bincount(spec["g2m_edge_index"][1]).unique().numel() > 1
+    assert torch.bincount(spec["m2m_edge_index"][1]).unique().numel() > 1
+    hspec = synthetic.make_graph_spec(30, 27, hierarchical=True)
+    for ei in hspec["mesh_down_edge_index"]:
+        d = torch.bincount(ei[1])
+        assert d.min().item() == d.max().item() == 1
