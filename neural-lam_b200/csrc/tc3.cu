@@ -537,6 +537,18 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
   int n_my = 0;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
   const int n_sub = n_my * d;
+  // work item -> (batch, receiver tile).  With batch-broadcast edge features the B batches of one tile are adjacent
+  // work items (processed by neighbouring CTAs at about the same time), so the tile's edge slices are fetched from
+  // DRAM once and hit L2 for the other batches; batched edge features keep tiles of one batch adjacent.
+  auto work_bt = [&](int w, int& b, int& t) {
+    if (p.e_batched) {
+      b = w / p.n_tiles;
+      t = w - b * p.n_tiles;
+    } else {
+      t = w / p.B;
+      b = w - t * p.B;
+    }
+  };
 
   if (warp == W_RING) {
     // =============================== operand ring: receiver tile, then d edge slices, per tile ===============
@@ -550,12 +562,14 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       int i = 0;
       for (int ti = 0; ti < n_my; ++ti) {
         const int w = blockIdx.x + ti * gridDim.x;
-        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        int b, t;
+        work_bt(w, b, t);
         const int r0 = t * 128;
         if (p.prefetch && ti + 1 < n_my) {
           // pull the next tile's operands into L2 while this one is processed
           const int wn = w + gridDim.x;
-          const int bn = wn / p.n_tiles, tn = wn - bn * p.n_tiles;
+          int bn, tn;
+          work_bt(wn, bn, tn);
           tma_prefetch_3d(&tmRec, 0, tn * 128, p.rec_batched ? bn : 0);
           tma_prefetch_3d(&tmRec, 32, tn * 128, p.rec_batched ? bn : 0);
           for (int k = 0; k < d; ++k) {
@@ -587,7 +601,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     const int grp4 = gt & 31, jb = gt >> 5;
     for (int ti = 0; ti < n_my; ++ti) {
       const int w = blockIdx.x + ti * gridDim.x;
-      const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+      int b, t;
+      work_bt(w, b, t);
       const int ngrp = __ldg(p.win_nu + t) >> 2;
       int4 ids = make_int4(0, 0, 0, 0);
       if (grp4 < ngrp) ids = __ldg(reinterpret_cast<const int4*>(p.win_u + (size_t)t * 128) + grp4);
@@ -596,7 +611,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         if (ti >= 2) {
           // the buffer holds the staged aggregate of tile ti-2: store it, then reuse the buffer
           const int wp = w - 2 * gridDim.x;
-          const int bp = wp / p.n_tiles, tp = wp - bp * p.n_tiles;
+          int bp, tp;
+          work_bt(wp, bp, tp);
           mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)(((ti - 2) >> 1) & 1));
           const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
           tma_store_3d(&tmOut, src, 0, tp * 128, bp);
@@ -616,7 +632,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     if (gt == 0) {
       for (int ti = (n_my >= 2 ? n_my - 2 : 0); ti < n_my; ++ti) {  // the last tiles' aggregates
         const int w = blockIdx.x + ti * gridDim.x;
-        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        int b, t;
+        work_bt(w, b, t);
         mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
         const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
         tma_store_3d(&tmOut, src, 0, t * 128, b);
@@ -719,12 +736,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     const int row = q * 32 + lane;
     const int c0 = half * 32;
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    // window row of this thread's edge in sub-tile j (prefetched one sub-tile ahead)
-    auto load_loc = [&](int j) -> int {
-      if (j >= n_sub) return 0;
-      const int ti = j / d, k = j - ti * d;
-      const int w = blockIdx.x + ti * gridDim.x;
-      const int t = w % p.n_tiles;
+    // window row of this thread's edge of neighbour slot k of receiver tile t (prefetched one sub-tile ahead)
+    auto load_loc = [&](int t, int k) -> int {
       const long long r = (long long)t * 128 + row;
       return (r < p.n_rec) ? (int)__ldg(p.loc + r * d + k) : 0;
     };
@@ -746,12 +759,23 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       mbar_arrive(bar_wscaled);
     }
     const float2 half2 = make_float2(0.5f, 0.5f);
-    int loc_next = load_loc(0);
+    int t_cur = 0, t_nxt = 0;
+    {
+      int bb;
+      if (n_my > 0) work_bt(blockIdx.x, bb, t_cur);
+    }
+    int loc_next = n_my > 0 ? load_loc(t_cur, 0) : 0;
     int ti = 0, k = 0;
     for (int j = 0; j < n_sub; ++j) {
       const int ts = j % NT;
       const int loc = loc_next;
-      loc_next = load_loc(j + 1);
+      if (k + 1 < d) {
+        loc_next = load_loc(t_cur, k + 1);
+      } else if (ti + 1 < n_my) {  // first sub-tile of the CTA's next tile
+        int bb;
+        work_bt(blockIdx.x + (ti + 1) * gridDim.x, bb, t_nxt);
+        loc_next = load_loc(t_nxt, 0);
+      }
       if (lead) {
         if (k == 0) {
           mbar_wait(bar_dr_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
@@ -792,6 +816,7 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       if (++k == d) {
         k = 0;
         ++ti;
+        t_cur = t_nxt;
       }
     }
   } else {
