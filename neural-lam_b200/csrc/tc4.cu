@@ -77,16 +77,6 @@ struct Row64Params {
     if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = clock64();     \
   } while (0)
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-// warp-uniform barrier test (every lane tests; lane 0's answer is taken so the compiler sees a uniform value)
-__device__ __forceinline__ bool mbar_test_u(uint32_t bar, uint32_t parity) {
-  return __shfl_sync(0xffffffffu, (int)mbar_test(bar, parity), 0) != 0;
-}
-
 __global__ void __launch_bounds__(r4::THREADS, 1)
 tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,

@@ -66,15 +66,6 @@ struct Edge3Params {
     if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = clock64();     \
   } while (0)
 
-__device__ __forceinline__ bool elect_one5() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ bool mbar_test_u5(uint32_t bar, uint32_t parity) {
-  return __shfl_sync(0xffffffffu, (int)mbar_test(bar, parity), 0) != 0;
-}
-
 __global__ void __launch_bounds__(e5::THREADS, 1)
 tc_edge3_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
@@ -238,12 +229,12 @@ tc_edge3_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       if (g1 < n_my && g1 <= g2 + 2) {
         const int s = g1 % NS;
         // a filled stage implies that tile g1-3 has left it, i.e. its accumulators were drained long ago
-        if (mbar_test_u5(bar_full + 8 * s, (uint32_t)((g1 / NS) & 1))) {
+        if (mbar_test_u(bar_full + 8 * s, (uint32_t)((g1 / NS) & 1))) {
           tc_fence_after();
           if (lane == 0) E5_DBG(1, g1);
           const uint32_t dd = tmem_base + s * 128;
           const uint64_t a0 = desc_st + (uint64_t)((s * 4 * BLK) >> 4);
-          if (elect_one5()) {
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -259,12 +250,12 @@ tc_edge3_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
       }
       if (g2 < g1) {
         const int s = g2 % NS;
-        if (mbar_test_u5(bar_hb_full + 8 * s, (uint32_t)((g2 / NS) & 1))) {
+        if (mbar_test_u(bar_hb_full + 8 * s, (uint32_t)((g2 / NS) & 1))) {
           tc_fence_after();
           if (lane == 0) E5_DBG(2, g2);
           const uint32_t dd = tmem_base + s * 128;
           const uint32_t ht = dd + 64;
-          if (elect_one5()) {
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll

@@ -53,6 +53,17 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// one elected lane of a converged warp (the warp stays in uniform control flow, so tcgen05.mma / TMA operands live in
+// uniform registers instead of going through an R2UR + waterfall loop per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform barrier test (every lane tests; lane 0's answer is taken so the compiler sees a uniform value)
+__device__ __forceinline__ bool mbar_test_u(uint32_t bar, uint32_t parity) {
+  return __shfl_sync(0xffffffffu, (int)mbar_test(bar, parity), 0) != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
