@@ -199,9 +199,20 @@ def save_graph(spec, graph_dir):
         f.write("spec_version: '1.0'\n")
 
 
-def load_graph(graph_dir, grid_xy):
+def load_graph(graph_dir, grid_xy, use_csr_cache=True):
     """Read a graph directory in the reference's current on-disk format (the file set
-    ``load_graph`` reads, reference utils/graph.py:146-422) into an unnormalised spec."""
+    ``load_graph`` reads, reference utils/graph.py:146-422) into an unnormalised spec.  If ``save_graph_csr_cache`` has
+    been run on the directory, every edge set (and its static features) is returned receiver-sorted."""
+    spec = _load_graph_raw(graph_dir, grid_xy)
+    if use_csr_cache:
+        for k in _EDGE_SETS:
+            if f"{k}_edge_index" in spec and (not isinstance(spec[f"{k}_edge_index"], list) or spec[f"{k}_edge_index"]):
+                spec[f"{k}_edge_index"], spec[f"{k}_features"] = _apply_csr_cache(graph_dir, k, spec[f"{k}_edge_index"],
+                                                                                  spec[f"{k}_features"])
+    return spec
+
+
+def _load_graph_raw(graph_dir, grid_xy):
     def ld(fn):
         return torch.load(os.path.join(graph_dir, fn), map_location="cpu", weights_only=True)
 
@@ -220,6 +231,52 @@ def load_graph(graph_dir, grid_xy):
         spec.update(m2m_edge_index=m2m_ei[0], m2m_features=m2m_f[0], mesh_static_features=mesh_f[0],
                     mesh_up_edge_index=[], mesh_up_features=[], mesh_down_edge_index=[], mesh_down_features=[])
     return spec
+
+
+_EDGE_SETS = ("g2m", "m2g", "m2m", "mesh_up", "mesh_down")
+
+
+def save_graph_csr_cache(graph_dir):
+    """Cached CSR next to the reference's ``.pt`` files: for every edge set of the graph
+    directory write ``<set>_csr.pt`` = {"order": stable receiver-sort permutation of the stored edge order (int64),
+    "rowptr": receiver CSR offsets (int32), "n_edges": E} — per level for the list-valued sets.  ``load_graph``
+    applies it, so that edges and their static features arrive in the kernels' storage order (receiver-sorted CSR)
+    without sorting at model construction."""
+    def ld(fn):
+        return torch.load(os.path.join(graph_dir, fn), map_location="cpu", weights_only=True)
+
+    for k in _EDGE_SETS:
+        fn = os.path.join(graph_dir, f"{k}_edge_index.pt")
+        if not os.path.isfile(fn):
+            continue
+        ei = ld(f"{k}_edge_index.pt")
+        as_list = isinstance(ei, (list, tuple))
+        entries = []
+        for e in (ei if as_list else [ei]):
+            rcv = e[1].long()
+            order = torch.sort(rcv, stable=True).indices
+            n_rec = int(rcv.max()) + 1 if rcv.numel() else 0
+            rowptr = torch.zeros(n_rec + 1, dtype=torch.int32)
+            rowptr[1:] = torch.cumsum(torch.bincount(rcv, minlength=n_rec), 0).to(torch.int32)
+            entries.append({"order": order, "rowptr": rowptr, "n_edges": int(e.shape[1])})
+        torch.save(entries if as_list else entries[0], os.path.join(graph_dir, f"{k}_csr.pt"))
+
+
+def _apply_csr_cache(graph_dir, name, edge_index, features):
+    """Permute one edge set (or list of levels) into its cached receiver-sorted order; stale or missing caches
+    (edge count mismatch) are ignored."""
+    fn = os.path.join(graph_dir, f"{name}_csr.pt")
+    if not os.path.isfile(fn):
+        return edge_index, features
+    cache = torch.load(fn, map_location="cpu", weights_only=True)
+    as_list = isinstance(edge_index, (list, tuple))
+    eis, fs = (list(edge_index), list(features)) if as_list else ([edge_index], [features])
+    caches = list(cache) if isinstance(cache, (list, tuple)) else [cache]
+    if len(caches) != len(eis) or any(c["n_edges"] != e.shape[1] for c, e in zip(caches, eis)):
+        return edge_index, features
+    eis = [e[:, c["order"]] for c, e in zip(caches, eis)]
+    fs = [f[c["order"]] for c, f in zip(caches, fs)]
+    return (eis, fs) if as_list else (eis[0], fs[0])
 
 
 class SyntheticDatastore:

@@ -87,3 +87,42 @@ def test_synthetic_graph_degrees_match_the_kernel_selection():
     for ei in hspec["mesh_down_edge_index"]:
         d = torch.bincount(ei[1])
         assert d.min().item() == d.max().item() == 1
+
+
+@pytest.mark.parametrize("hier", [False, True])
+def test_graph_csr_cache_roundtrip(tmp_path, hier):
+    """Cached CSR next to the reference-format graph files: loading applies the stored permutation, the
+    result equals sorting at load time, and a stale cache is ignored."""
+    import os
+
+    import torch
+    from neural_lam_b200 import synthetic
+    from neural_lam_b200.models import _sort_edges
+
+    spec = synthetic.make_graph_spec(30, 27, hierarchical=hier)
+    assert spec["hierarchical"] == hier
+    # shuffle one edge set so that the stored order is NOT receiver-sorted
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(spec["g2m_edge_index"].shape[1], generator=g)
+    spec["g2m_edge_index"], spec["g2m_features"] = spec["g2m_edge_index"][:, perm], spec["g2m_features"][perm]
+    d = str(tmp_path / "graph")
+    synthetic.save_graph(spec, d)
+    raw = synthetic.load_graph(d, spec["grid_xy"])
+    assert torch.equal(raw["g2m_edge_index"], spec["g2m_edge_index"])  # no cache yet: stored order
+    synthetic.save_graph_csr_cache(d)
+    got = synthetic.load_graph(d, spec["grid_xy"])
+    for k in ("g2m", "m2g"):
+        ei, f = _sort_edges(raw[f"{k}_edge_index"], raw[f"{k}_features"])
+        assert torch.equal(got[f"{k}_edge_index"], ei) and torch.equal(got[f"{k}_features"], f)
+        assert bool((got[f"{k}_edge_index"][1][1:] >= got[f"{k}_edge_index"][1][:-1]).all())
+    m2m_raw = raw["m2m_edge_index"] if hier else [raw["m2m_edge_index"]]
+    m2m_got = got["m2m_edge_index"] if hier else [got["m2m_edge_index"]]
+    for a, b in zip(m2m_raw, m2m_got):
+        assert torch.equal(b, a[:, torch.sort(a[1], stable=True).indices])
+    cache = torch.load(os.path.join(d, "g2m_csr.pt"), weights_only=True)
+    assert cache["rowptr"][-1].item() == cache["n_edges"] == raw["g2m_edge_index"].shape[1]
+    # stale cache (edge count changed): ignored
+    torch.save(raw["g2m_edge_index"][:, :-1], os.path.join(d, "g2m_edge_index.pt"))
+    torch.save(raw["g2m_features"][:-1], os.path.join(d, "g2m_features.pt"))
+    stale = synthetic.load_graph(d, spec["grid_xy"])
+    assert torch.equal(stale["g2m_edge_index"], raw["g2m_edge_index"][:, :-1])
