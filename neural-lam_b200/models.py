@@ -22,6 +22,7 @@ from torch import nn
 
 from . import _lib, ops
 from .gnn_layers import InteractionNet, get_gnn_class
+from .clamping import OutputClamp
 from .networks import GNNSequential, make_mlp
 from .synthetic import normalize_graph
 
@@ -61,13 +62,18 @@ class StepPredictor(nn.Module):
     """One-step predictor ``(X_{t-1}, X_t, forcing_t) -> X_{t+1}`` (reference
     models/step_predictors/base.py)."""
 
-    def __init__(self, datastore, output_std=False):
+    def __init__(self, datastore, output_std=False, output_clamping_lower=None, output_clamping_upper=None):
         super().__init__()
         self.register_buffer("grid_static_features", datastore.grid_static_features.float(), persistent=False)
         self.num_grid_nodes = self.grid_static_features.shape[0]
         self.num_state_vars = datastore.num_state_vars
         self.output_std = bool(output_std)
         self.grid_output_dim = 2 * self.num_state_vars if self.output_std else self.num_state_vars
+        # output clamping (reference step_predictors/base.py:56-61, :181-334): {state variable name: physical limit}
+        self.output_clamp = None
+        if output_clamping_lower or output_clamping_upper:
+            self.output_clamp = OutputClamp(list(datastore.state_var_names), output_clamping_lower, output_clamping_upper,
+                                            datastore.state_mean, datastore.state_std)
 
     @property
     def predicts_std(self):
@@ -77,9 +83,15 @@ class StepPredictor(nn.Module):
         """(N,d) -> (B,N,d) stride-0 view (reference step_predictors/base.py:122-139)."""
         return x.unsqueeze(0).expand(batch_size, -1, -1)
 
+    @property
+    def clamps_output(self):
+        return self.output_clamp is not None and self.output_clamp.active
+
     def get_clamped_new_state(self, state_delta, prev_state):
-        """No clamping limits configured -> plain residual update (reference
-        step_predictors/base.py:366 with empty index lists)."""
+        """``X_{t+1} = f(f^-1(X_t) + delta)`` for the variables with configured limits, the plain residual update for
+        the others (reference step_predictors/base.py:335-396); with no limits the index lists are empty."""
+        if self.clamps_output:
+            return self.output_clamp(state_delta, prev_state)
         return prev_state + state_delta
 
 
@@ -88,8 +100,9 @@ class BaseGraphModel(StepPredictor):
 
     def __init__(self, datastore, graph, hidden_dim=64, hidden_layers=1, processor_layers=4, mesh_aggr="sum",
                  output_std=False, g2m_gnn_type="InteractionNet", m2g_gnn_type="InteractionNet", math=None,
-                 **_unused):
-        super().__init__(datastore, output_std=output_std)
+                 output_clamping_lower=None, output_clamping_upper=None, **_unused):
+        super().__init__(datastore, output_std=output_std, output_clamping_lower=output_clamping_lower,
+                         output_clamping_upper=output_clamping_upper)
         self.g2m_gnn_type, self.m2g_gnn_type = g2m_gnn_type, m2g_gnn_type
         self.register_buffer("diff_mean", datastore.state_diff_mean.float(), persistent=False)
         self.register_buffer("diff_std", datastore.state_diff_std.float(), persistent=False)
@@ -185,7 +198,7 @@ class BaseGraphModel(StepPredictor):
         grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)  # base.py:308-310
         mesh_rep = self.process_step(mesh_rep, st)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
-        if not torch.is_grad_enabled() and not self.output_std:
+        if not torch.is_grad_enabled() and not self.output_std and not self.clamps_output:
             # output_map + rescale (base.py:339) + residual (base.py:342) in one launch where the library fuses it
             fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, None, None, self.diff_std, self.diff_mean,
                                     flags=self.output_map.nlam_flags)
@@ -197,7 +210,7 @@ class BaseGraphModel(StepPredictor):
             pred_std = torch.nn.functional.softplus(pred_std_raw)
         else:
             pred_delta_mean, pred_std = net_output, None
-        if not torch.is_grad_enabled() and not self.output_std:
+        if not torch.is_grad_enabled() and not self.output_std and not self.clamps_output:
             # rescale (base.py:339) + residual (base.py:342) in one kernel
             return ops.step_epilogue(pred_delta_mean, prev_state, None, None, self.diff_std, self.diff_mean), None
         rescaled = pred_delta_mean * self.diff_std + self.diff_mean
@@ -208,6 +221,10 @@ class BaseGraphModel(StepPredictor):
         """Inference step with the ARForecaster boundary mix (autoregressive.py:128-131) fused
         into the step epilogue kernel.  ``out``: optional preallocated (B,G,d) tensor for the new state."""
         assert not self.output_std
+        if self.clamps_output:  # clamped update (elementwise torch ops), then the boundary mix
+            pred, _ = self.forward(prev_state, prev_prev_state, forcing)
+            new_state = boundary_mask * boundary_state + (1.0 - boundary_mask) * pred
+            return new_state if out is None else out.copy_(new_state)
         B = prev_state.shape[0]
         grid_emb = self.grid_embedder.apply_rows(
             [prev_state, prev_prev_state, forcing, self.expand_to_batch(self.grid_static_features, B)])
@@ -233,7 +250,9 @@ class GraphLAM(BaseGraphModel):
                  **kwargs):
         super().__init__(datastore, graph, hidden_dim=hidden_dim, hidden_layers=hidden_layers,
                          processor_layers=processor_layers, mesh_aggr=mesh_aggr, output_std=output_std,
-                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math)
+                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math,
+                         output_clamping_lower=kwargs.get("output_clamping_lower"),
+                         output_clamping_upper=kwargs.get("output_clamping_upper"))
         assert not self.hierarchical, "GraphLAM does not use a hierarchical mesh graph"
         mesh_dim = self.mesh_static_features.shape[1]
         m2m_dim = self.m2m_features.shape[1]
@@ -275,7 +294,9 @@ class BaseHiGraphModel(BaseGraphModel):
                  mesh_up_gnn_type="InteractionNet", mesh_down_gnn_type="InteractionNet", math=None, **kwargs):
         super().__init__(datastore, graph, hidden_dim=hidden_dim, hidden_layers=hidden_layers,
                          processor_layers=processor_layers, mesh_aggr=mesh_aggr, output_std=output_std,
-                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math)
+                         g2m_gnn_type=g2m_gnn_type, m2g_gnn_type=m2g_gnn_type, math=math,
+                         output_clamping_lower=kwargs.get("output_clamping_lower"),
+                         output_clamping_upper=kwargs.get("output_clamping_upper"))
         assert self.hierarchical, "hierarchical models need a hierarchical mesh graph"
         self.mesh_up_gnn_type, self.mesh_down_gnn_type = mesh_up_gnn_type, mesh_down_gnn_type
         self.num_levels = len(self.mesh_static_features)

@@ -297,6 +297,10 @@ class SyntheticDatastore:
         self.grid_static_features = torch.randn(self.num_grid_nodes, d_static, generator=g)
         self.state_diff_mean = torch.zeros(d_state)
         self.state_diff_std = torch.ones(d_state)
+        # standardisation statistics and names of the state variables (used by output clamping only)
+        self.state_mean = torch.zeros(d_state)
+        self.state_std = torch.ones(d_state)
+        self.state_var_names = [f"var{i}" for i in range(d_state)]
         m = torch.zeros(Nx, Ny)
         w = min(boundary_width, max(1, min(Nx, Ny) // 4))
         m[:w, :] = 1

@@ -274,3 +274,44 @@ def algorithmic_bytes_inet(B, Ns, Nr, E, H, update_edges, same_nodes):
 def flops_inet(B, Nr, E, H):
     """forward FLOPs (LayerNorm/SiLU excluded)."""
     return B * (8 * H * H * E + 6 * H * H * Nr)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Output clamping (models/step_predictors/base.py:181-396 with utils/tensor.py:7-81)
+# ---------------------------------------------------------------------------------------------------
+def ref_inverse_softplus(x, beta=1.0, threshold=20.0):
+    """utils/tensor.py:7-50."""
+    x_clamped = torch.clamp(x, min=torch.log(torch.tensor(1e-6 + 1)) / beta, max=threshold / beta)
+    non_linear_part = torch.log(torch.expm1(x_clamped * beta)) / beta
+    below_threshold = x * beta <= threshold
+    return torch.where(below_threshold, non_linear_part, x)
+
+
+def ref_inverse_sigmoid(x):
+    """utils/tensor.py:53-81."""
+    x_clamped = torch.clamp(x, min=1e-6, max=1 - 1e-6)
+    return torch.log(x_clamped / (1 - x_clamped))
+
+
+def clamped_new_state(state_delta, prev_state, names, lower, upper, state_mean, state_std):
+    """``prepare_clamping_params`` + ``get_clamped_new_state`` (step_predictors/base.py:181-396): per state variable
+    with both limits a scaled sigmoid, lower-only / upper-only a shifted softplus, applied as f(f^-1(X_t) + delta);
+    limits standardised with the state statistics (:229-234); sharpness 1 and centre 0 (:217-220)."""
+    new_state = prev_state + state_delta
+    for i, n in enumerate(names):
+        has_lo, has_up = n in lower, n in upper
+        if not (has_lo or has_up):
+            continue
+        lo = (lower[n] - state_mean[i]) / state_std[i] if has_lo else None
+        up = (upper[n] - state_mean[i]) / state_std[i] if has_up else None
+        x, d = prev_state[:, :, i], state_delta[:, :, i]
+        if has_lo and has_up:
+            z = 0 + ref_inverse_sigmoid((x - lo) / (up - lo)) / 1 + d                       # :316-322
+            new_state[:, :, i] = lo + (up - lo) * torch.sigmoid(1 * (z - 0))              # :296-300
+        elif has_lo:
+            z = ref_inverse_softplus(x - lo, beta=1) + 0 + d                              # :323-328
+            new_state[:, :, i] = lo + torch.nn.functional.softplus(z - 0, beta=1)         # :301-306
+        else:
+            z = -ref_inverse_softplus(up - x, beta=1) + 0 + d                             # :329-334
+            new_state[:, :, i] = up - torch.nn.functional.softplus(0 - z, beta=1)         # :307-312
+    return new_state
