@@ -1,11 +1,16 @@
-"""Importable alias for the package directory ``neural-lam_b200/`` (a hyphen is not a valid
-Python identifier, so ``import neural_lam_b200`` resolves here and executes the real package
-``__init__`` with ``__path__`` pointing at ``neural-lam_b200/``)."""
-import os as _os
+"""neural_lam_b200 — B200 (sm_100a) kernels for Neural-LAM's InteractionNet message-passing
+hot path behind the reference's Python API (``neural_lam.gnn_layers`` /
+``neural_lam.models`` GraphLAM / HiLAM).  See DESIGN.md and INTEGRATION.md."""
+from . import _lib, ops  # noqa: F401
+from .gnn_layers import (  # noqa: F401
+    GNN_TYPES,
+    InteractionNet,
+    PropagationNet,
+    SplitMLPs,
+    get_default_math,
+    get_gnn_class,
+    set_default_math,
+)
+from .networks import make_gnn_seq, make_mlp  # noqa: F401
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "neural-lam_b200")
-__path__ = [_real]
-__file__ = _os.path.join(_real, "__init__.py")
-with open(__file__, encoding="utf-8") as _f:
-    exec(compile(_f.read(), __file__, "exec"), globals())
-del _f, _os
+__version__ = "0.1.0"

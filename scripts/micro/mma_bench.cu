@@ -1,6 +1,6 @@
 // Micro-benchmark: cycles per tcgen05.mma kind::tf32 instruction (M=128, K=8) as a function of N,
 // operand form (SS: A from shared memory, TS: A from TMEM) — one CTA per SM, back-to-back issue.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I neural-lam_b200/csrc -I include scripts/micro/mma_bench.cu -o gpurun_out/mma_bench
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I neural_lam_b200/csrc -I include scripts/micro/mma_bench.cu -o gpurun_out/mma_bench
 #include "tc_ptx.cuh"
 using namespace nlam;
 
