@@ -64,9 +64,23 @@ class OutputClamp(nn.Module):
 
     @property
     def active(self):
-        return (self.clamp_lower_upper_idx.numel() + self.clamp_lower_idx.numel() + self.clamp_upper_idx.numel()) > 0
+        return clamp_active(self)
 
     def forward(self, state_delta, prev_state):
+        return clamped_update(self, state_delta, prev_state)
+
+
+BUFFER_NAMES = ("sigmoid_lower_lims", "sigmoid_upper_lims", "softplus_lower_lims", "softplus_upper_lims",
+                "clamp_lower_upper_idx", "clamp_lower_idx", "clamp_upper_idx")
+
+
+def clamp_active(self):
+    """``self``: any module holding the seven clamping buffers (an ``OutputClamp`` or, as in the reference where
+    ``prepare_clamping_params`` registers them on the predictor itself, a step predictor)."""
+    return (self.clamp_lower_upper_idx.numel() + self.clamp_lower_idx.numel() + self.clamp_upper_idx.numel()) > 0
+
+
+def clamped_update(self, state_delta, prev_state):
         """``get_clamped_new_state`` (step_predictors/base.py:335-396); sharpness 1, centre 0 as in the reference."""
         new_state = prev_state + state_delta
         if self.clamp_lower_upper_idx.numel() > 0:

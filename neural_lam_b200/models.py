@@ -22,6 +22,7 @@ from torch import nn
 
 from . import _lib, ops
 from .gnn_layers import InteractionNet, get_gnn_class
+from . import clamping
 from .clamping import OutputClamp
 from .networks import GNNSequential, make_mlp
 from .synthetic import normalize_graph
@@ -69,11 +70,13 @@ class StepPredictor(nn.Module):
         self.num_state_vars = datastore.num_state_vars
         self.output_std = bool(output_std)
         self.grid_output_dim = 2 * self.num_state_vars if self.output_std else self.num_state_vars
-        # output clamping (reference step_predictors/base.py:56-61, :181-334): {state variable name: physical limit}
-        self.output_clamp = None
-        if output_clamping_lower or output_clamping_upper:
-            self.output_clamp = OutputClamp(list(datastore.state_var_names), output_clamping_lower, output_clamping_upper,
-                                            datastore.state_mean, datastore.state_std)
+        # output clamping (reference step_predictors/base.py:56-61, :181-334): {state variable name: physical limit}.
+        # As in the reference (``prepare_clamping_params``, :279-301) the seven limit / index buffers are PERSISTENT
+        # buffers of the predictor itself — empty when no limits are configured — so its checkpoints load strictly.
+        clamp = OutputClamp(list(datastore.state_var_names), output_clamping_lower, output_clamping_upper,
+                            datastore.state_mean, datastore.state_std)
+        for name in clamping.BUFFER_NAMES:
+            self.register_buffer(name, getattr(clamp, name))
 
     @property
     def predicts_std(self):
@@ -85,13 +88,13 @@ class StepPredictor(nn.Module):
 
     @property
     def clamps_output(self):
-        return self.output_clamp is not None and self.output_clamp.active
+        return clamping.clamp_active(self)
 
     def get_clamped_new_state(self, state_delta, prev_state):
         """``X_{t+1} = f(f^-1(X_t) + delta)`` for the variables with configured limits, the plain residual update for
         the others (reference step_predictors/base.py:335-396); with no limits the index lists are empty."""
         if self.clamps_output:
-            return self.output_clamp(state_delta, prev_state)
+            return clamping.clamped_update(self, state_delta, prev_state)
         return prev_state + state_delta
 
 
@@ -412,7 +415,41 @@ class HiLAM(BaseHiGraphModel):
         return levels, same, up, down
 
 
-MODELS = {"graph_lam": GraphLAM, "hi_lam": HiLAM}
+class HiLAMParallel(BaseHiGraphModel):
+    """Hierarchical model whose processor runs all same-level / up / down message passing of the mesh hierarchy
+    as ONE InteractionNet over the concatenated node sets and edge sets, with separate MLPs per edge set and per
+    level (reference graph/hi_lam_parallel.py: index offsets :89-122, processor :124-143,
+    hi_processor_step :145-218)."""
+
+    def __init__(self, datastore, graph, **kwargs):
+        super().__init__(datastore, graph, **kwargs)
+        first = [0]
+        for size in self.level_mesh_sizes[:-1]:
+            first.append(first[-1] + size)
+        total = [ei + off for ei, off in zip(self.m2m_edge_index, first)]
+        total += [torch.stack((ei[0] + first[l], ei[1] + first[l + 1])) for l, ei in enumerate(self.mesh_up_edge_index)]
+        total += [torch.stack((ei[0] + first[l + 1], ei[1] + first[l])) for l, ei in enumerate(self.mesh_down_edge_index)]
+        self.edge_split_sections = [ei.shape[1] for ei in total]
+        total_edge_index = torch.cat(total, dim=1)
+        self.processor = GNNSequential([
+            InteractionNet(total_edge_index, self.hidden_dim, hidden_layers=self.hidden_layers,
+                           edge_chunk_sizes=self.edge_split_sections, aggr_chunk_sizes=self.level_mesh_sizes,
+                           math=self.math)
+            for _ in range(self.processor_layers)])
+        self._set_mlp_flags()
+
+    def hi_processor_step(self, levels, same, up, down):
+        """reference graph/hi_lam_parallel.py:186-218"""
+        L = self.num_levels
+        mesh_rep = torch.cat(levels, dim=1)
+        edge_rep = torch.cat(list(same) + list(up) + list(down), dim=1)
+        mesh_rep, edge_rep = self.processor(mesh_rep, edge_rep)
+        levels = list(torch.split(mesh_rep, self.level_mesh_sizes, dim=1))
+        sections = torch.split(edge_rep, self.edge_split_sections, dim=1)
+        return levels, list(sections[:L]), list(sections[L:2 * L - 1]), list(sections[2 * L - 1:])
+
+
+MODELS = {"graph_lam": GraphLAM, "hi_lam": HiLAM, "hi_lam_parallel": HiLAMParallel}
 
 
 class ARForecaster(nn.Module):

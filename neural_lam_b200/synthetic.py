@@ -156,6 +156,10 @@ def make_graph_spec(Nx, Ny, hierarchical=False, n_levels=None, spacing=1.0):
     return spec
 
 
+GRAPH_SPEC_VERSION = "0.1.0"  # reference create_graph.py:25 CURRENT_GRAPH_SPEC_VERSION; file name :24
+METAINFO_FILENAME = "metainfo.yaml"
+
+
 def normalize_graph(spec):
     """What ``load_graph`` does to the on-disk tensors (reference utils/graph.py:291-303,
     :343-350): mesh coordinates / max grid span, edge features / longest m2m edge."""
@@ -165,14 +169,27 @@ def normalize_graph(spec):
     span = span if span != 0 else 1.0
     hier = spec["hierarchical"]
     m2m_f = spec["m2m_features"] if hier else [spec["m2m_features"]]
-    longest = max(float(f[:, 0].max()) for f in m2m_f)
+    # bit-for-bit what the reference's load_graph computes (utils/graph.py:343-350, :390-394): the per-level sets
+    # (BufferList ``/=``, buffer_list.py:93) are MULTIPLIED by the float32 reciprocal of the longest m2m edge, the
+    # g2m / m2g features are divided by it
+    longest = max(torch.max(f[:, 0]) for f in m2m_f)
+    inv_longest = 1.0 / longest
+    def scale_xy(m):
+        # only the two coordinate columns are scaled (utils/graph.py:302-303 ``m[:, :2] /= scaling``); legacy
+        # graphs store normalised mesh coordinates already (:284-289)
+        if spec.get("legacy"):
+            return m
+        m = m.clone()
+        m[:, :2] /= span
+        return m
+
     if hier:
-        out["mesh_static_features"] = [m / span for m in spec["mesh_static_features"]]
+        out["mesh_static_features"] = [scale_xy(m) for m in spec["mesh_static_features"]]
         for k in ("m2m_features", "mesh_up_features", "mesh_down_features"):
-            out[k] = [f / longest for f in spec[k]]
+            out[k] = [f * inv_longest for f in spec[k]]
     else:
-        out["mesh_static_features"] = spec["mesh_static_features"] / span
-        out["m2m_features"] = spec["m2m_features"] / longest
+        out["mesh_static_features"] = scale_xy(spec["mesh_static_features"])
+        out["m2m_features"] = spec["m2m_features"] * inv_longest
     out["g2m_features"] = spec["g2m_features"] / longest
     out["m2g_features"] = spec["m2g_features"] / longest
     out["normalized"] = True
@@ -196,7 +213,7 @@ def save_graph(spec, graph_dir):
             torch.save(spec[f"{k}_edge_index"], os.path.join(graph_dir, f"{k}_edge_index.pt"))
             torch.save(spec[f"{k}_features"], os.path.join(graph_dir, f"{k}_features.pt"))
     with open(os.path.join(graph_dir, "metainfo.yaml"), "w", encoding="utf-8") as f:
-        f.write("spec_version: '1.0'\n")
+        f.write(f"spec_version: {GRAPH_SPEC_VERSION}\n")
 
 
 def load_graph(graph_dir, grid_xy, use_csr_cache=True):
@@ -212,20 +229,65 @@ def load_graph(graph_dir, grid_xy, use_csr_cache=True):
     return spec
 
 
+def _graph_spec_version(graph_dir):
+    """``spec_version`` of the directory's metainfo file, ``"legacy"`` if the file is missing (reference
+    utils/graph.py:227-262); a file without the entry, or an unknown version, is an error (:256-274)."""
+    path = os.path.join(graph_dir, METAINFO_FILENAME)
+    if not os.path.isfile(path):
+        return "legacy"
+    import yaml
+
+    with open(path, encoding="utf-8") as f:
+        meta = yaml.safe_load(f)
+    version = None if meta is None else meta.get("spec_version")
+    if version is None:
+        raise ValueError(f"{METAINFO_FILENAME} is missing 'spec_version' entry")
+    if str(version) != GRAPH_SPEC_VERSION:
+        raise ValueError(f"Unsupported graph spec version {version!r} in {METAINFO_FILENAME}")
+    return str(version)
+
+
+def _zero_index(ei):
+    """reference utils/graph.py:21-35"""
+    return ei - ei.min(dim=1, keepdim=True)[0]
+
+
 def _load_graph_raw(graph_dir, grid_xy):
     def ld(fn):
         return torch.load(os.path.join(graph_dir, fn), map_location="cpu", weights_only=True)
 
-    m2m_ei = ld("m2m_edge_index.pt")
-    hier = len(m2m_ei) > 1
-    spec = {"hierarchical": hier, "grid_xy": torch.as_tensor(grid_xy, dtype=torch.float32).reshape(-1, 2),
-            "g2m_edge_index": ld("g2m_edge_index.pt"), "m2g_edge_index": ld("m2g_edge_index.pt"),
-            "g2m_features": ld("g2m_features.pt"), "m2g_features": ld("m2g_features.pt")}
+    legacy = _graph_spec_version(graph_dir) == "legacy"
+    m2m_ei = list(ld("m2m_edge_index.pt"))
     m2m_f, mesh_f = ld("m2m_features.pt"), ld("mesh_features.pt")
+    g2m_ei, m2g_ei = ld("g2m_edge_index.pt"), ld("m2g_edge_index.pt")
+    up_ei = down_ei = None
+    hier = len(m2m_ei) > 1
     if hier:
-        spec.update(m2m_edge_index=list(m2m_ei), m2m_features=list(m2m_f), mesh_static_features=list(mesh_f),
-                    mesh_up_edge_index=list(ld("mesh_up_edge_index.pt")), mesh_up_features=list(ld("mesh_up_features.pt")),
-                    mesh_down_edge_index=list(ld("mesh_down_edge_index.pt")),
+        up_ei, down_ei = list(ld("mesh_up_edge_index.pt")), list(ld("mesh_down_edge_index.pt"))
+    if legacy:
+        # legacy directories label the nodes of all sets with one offset numbering and hold normalised mesh
+        # coordinates: zero-index every edge set on load (reference utils/graph.py:313-328, :368-374; the
+        # g2m / m2g rules :38-142 — not every mesh node needs to appear in them)
+        m2m_ei = [_zero_index(e) for e in m2m_ei]
+        n_mesh = sum(m.shape[0] for m in mesh_f)
+        mins = m2g_ei.min(dim=1)[0]
+        if bool(mins[0] < mins[1]):  # mesh nodes carry the first labels
+            g2m_ei = torch.stack((g2m_ei[0] - n_mesh, g2m_ei[1]))
+            m2g_ei = torch.stack((m2g_ei[0], m2g_ei[1] - n_mesh))
+        else:
+            g2m_ei = torch.stack((g2m_ei[0], g2m_ei[1] - (g2m_ei[0].max() + 1)))
+            m2g_ei = torch.stack((m2g_ei[0] - (m2g_ei[1].max() + 1), m2g_ei[1]))
+        if hier:
+            up_ei, down_ei = [_zero_index(e) for e in up_ei], [_zero_index(e) for e in down_ei]
+    if int(m2g_ei.min()) < 0 or int(g2m_ei.min()) < 0:
+        raise ValueError("negative node index in g2m / m2g edge_index")
+    spec = {"hierarchical": hier, "legacy": legacy, "grid_xy": torch.as_tensor(grid_xy, dtype=torch.float32).reshape(-1, 2),
+            "g2m_edge_index": g2m_ei, "m2g_edge_index": m2g_ei,
+            "g2m_features": ld("g2m_features.pt"), "m2g_features": ld("m2g_features.pt")}
+    if hier:
+        spec.update(m2m_edge_index=m2m_ei, m2m_features=list(m2m_f), mesh_static_features=list(mesh_f),
+                    mesh_up_edge_index=up_ei, mesh_up_features=list(ld("mesh_up_features.pt")),
+                    mesh_down_edge_index=down_ei,
                     mesh_down_features=list(ld("mesh_down_features.pt")))
     else:
         spec.update(m2m_edge_index=m2m_ei[0], m2m_features=m2m_f[0], mesh_static_features=mesh_f[0],
@@ -309,6 +371,7 @@ class SyntheticDatastore:
         m[:, -w:] = 1
         self.boundary_mask = m.reshape(-1, 1)
         gxy = spec["grid_xy"]
+        self.grid_xy = gxy
         self.grid_xy_max_span = float(max(gxy[:, 0].max() - gxy[:, 0].min(), gxy[:, 1].max() - gxy[:, 1].min()))
 
     @property

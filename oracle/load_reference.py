@@ -13,6 +13,7 @@ resolves to ``networks.py``.
 """
 import importlib.util
 import os
+import re
 import sys
 import types
 
@@ -26,32 +27,46 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "neural_lam", "gnn_layers.py"))
 
 
+def _load_file(name, relpath):
+    """exec one reference source file, unmodified, as module ``_PKG.name``."""
+    full = f"{_PKG}.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, os.path.join(REFERENCE_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    parent_name, _, leaf = full.rpartition(".")
+    setattr(sys.modules[parent_name], leaf, mod)
+    return mod
+
+
+def _synthetic_package(name):
+    full = f"{_PKG}.{name}" if name else _PKG
+    if full in sys.modules:
+        return sys.modules[full]
+    mod = types.ModuleType(full)
+    mod.__path__ = []  # mark as package
+    sys.modules[full] = mod
+    if name:
+        parent_name, _, leaf = full.rpartition(".")
+        setattr(sys.modules[parent_name], leaf, mod)
+    return mod
+
+
 def load():
     """Return a namespace with the reference ``InteractionNet``, ``PropagationNet``,
     ``SplitMLPs``, ``GNN_TYPES``, ``make_mlp`` loaded from the reference files."""
     if not available():
         raise FileNotFoundError(f"reference source not found under {REFERENCE_ROOT}")
-    if _PKG + ".gnn_layers" in sys.modules:
-        gl = sys.modules[_PKG + ".gnn_layers"]
-        nw = sys.modules[_PKG + ".utils"]
-    else:
-        pyg_standin.install()
-        parent = types.ModuleType(_PKG)
-        parent.__path__ = []  # mark as package
-        sys.modules[_PKG] = parent
-
-        def _load(name, relpath):
-            spec = importlib.util.spec_from_file_location(
-                f"{_PKG}.{name}", os.path.join(REFERENCE_ROOT, relpath)
-            )
-            mod = importlib.util.module_from_spec(spec)
-            sys.modules[f"{_PKG}.{name}"] = mod
-            spec.loader.exec_module(mod)
-            setattr(parent, name, mod)
-            return mod
-
-        nw = _load("utils", "neural_lam/utils/networks.py")
-        gl = _load("gnn_layers", "neural_lam/gnn_layers.py")
+    pyg_standin.install()
+    _synthetic_package("")
+    # ``neural_lam/utils/__init__.py`` pulls logging / plotting helpers (matplotlib, ...): the package
+    # object is synthetic and re-exports what the loaded files define, the FILES are the reference's
+    utils = _synthetic_package("utils")
+    nw = _load_file("utils.networks", "neural_lam/utils/networks.py")
+    utils.make_mlp, utils.make_gnn_seq = nw.make_mlp, nw.make_gnn_seq
+    gl = _load_file("gnn_layers", "neural_lam/gnn_layers.py")
     ns = types.SimpleNamespace(
         InteractionNet=gl.InteractionNet,
         PropagationNet=gl.PropagationNet,
@@ -62,6 +77,103 @@ def load():
         gnn_layers=gl,
         networks=nw,
     )
+    return ns
+
+
+class _Values:
+    """The ``.values`` face of the xarray objects the step predictors read."""
+
+    def __init__(self, arr):
+        self.values = arr
+
+
+class StubDatastore:
+    """The ``BaseDatastore`` surface the reference's step predictors / ARForecaster touch
+    (step_predictors/base.py:62-106, :196; graph/base.py:86-135; utils/graph.py:443-446, :494-512;
+    forecasters/autoregressive.py:35-40), filled from a ``neural_lam_b200.synthetic.SyntheticDatastore``;
+    the graph is read by the reference's own ``load_graph`` from ``root_path/graph/<name>``."""
+
+    def __init__(self, ds, root_path):
+        import pathlib
+
+        self._ds = ds
+        self.root_path = pathlib.Path(root_path)
+        self.num_grid_points = ds.num_grid_nodes
+        self.boundary_mask = _Values(ds.boundary_mask.reshape(-1).numpy())
+
+    def get_num_data_vars(self, category):
+        return {"state": self._ds.num_state_vars, "forcing": self._ds.num_forcing_vars,
+                "static": self._ds.num_static_vars}[category]
+
+    def get_vars_names(self, category):
+        assert category == "state"
+        return list(self._ds.state_var_names)
+
+    def get_dataarray(self, category, split=None, standardize=False):
+        assert category == "static"
+        if self._ds.num_static_vars == 0:
+            return None
+        return _Values(self._ds.grid_static_features.numpy())
+
+    def get_standardization_dataarray(self, category):
+        assert category == "state"
+        d = self._ds
+        return types.SimpleNamespace(
+            state_mean=_Values(d.state_mean.numpy()), state_std=_Values(d.state_std.numpy()),
+            state_diff_mean_standardized=_Values(d.state_diff_mean.numpy()),
+            state_diff_std_standardized=_Values(d.state_diff_std.numpy()))
+
+    def get_xy_extent(self, category):
+        gxy = self._ds.grid_xy
+        return [float(gxy[:, 0].min()), float(gxy[:, 0].max()), float(gxy[:, 1].min()), float(gxy[:, 1].max())]
+
+
+def load_models():
+    """Load the reference's step predictors and forecaster UNMODIFIED:
+    ``models/step_predictors/base.py``, ``graph/{base,graph_lam,hierarchical,hi_lam,hi_lam_parallel}.py``,
+    ``models/forecasters/{base,autoregressive}.py``, ``utils/{graph,buffer_list,tensor}.py`` — under the
+    synthetic parent package, with stubs only for what those files import but never compute with here:
+    ``datastore.BaseDatastore`` (a type annotation), ``create_graph``'s two format constants (read from the
+    reference file), ``utils.log_on_rank_zero`` (a print).  Returns a namespace with the classes."""
+    ns = load()
+    pkg = sys.modules[_PKG]
+    utils = sys.modules[f"{_PKG}.utils"]
+    if not hasattr(pkg, "datastore"):
+        dsm = _synthetic_package("datastore")
+
+        class BaseDatastore:  # annotation only on the path
+            pass
+
+        dsm.BaseDatastore = BaseDatastore
+        cg = _synthetic_package("create_graph")
+        text = open(os.path.join(REFERENCE_ROOT, "neural_lam", "create_graph.py"), encoding="utf-8").read()
+        for const in ("METAINFO_FILENAME", "CURRENT_GRAPH_SPEC_VERSION"):
+            m = re.search(rf'^{const}\s*=\s*"([^"]+)"', text, re.M)
+            setattr(cg, const, m.group(1))
+    bl = _load_file("utils.buffer_list", "neural_lam/utils/buffer_list.py")
+    tn = _load_file("utils.tensor", "neural_lam/utils/tensor.py")
+    gr = _load_file("utils.graph", "neural_lam/utils/graph.py")
+    utils.BufferList = bl.BufferList
+    utils.inverse_sigmoid, utils.inverse_softplus = tn.inverse_sigmoid, tn.inverse_softplus
+    utils.load_graph, utils.load_and_register_graph = gr.load_graph, gr.load_and_register_graph
+    utils.compute_grid_input_dim = gr.compute_grid_input_dim
+    utils.log_on_rank_zero = lambda *a, **k: None
+    for sub in ("models", "models.step_predictors", "models.step_predictors.graph", "models.forecasters"):
+        _synthetic_package(sub)
+    sp = _load_file("models.step_predictors.base", "neural_lam/models/step_predictors/base.py")
+    gdir = "neural_lam/models/step_predictors/graph/"
+    gb = _load_file("models.step_predictors.graph.base", gdir + "base.py")
+    glam = _load_file("models.step_predictors.graph.graph_lam", gdir + "graph_lam.py")
+    hier = _load_file("models.step_predictors.graph.hierarchical", gdir + "hierarchical.py")
+    hil = _load_file("models.step_predictors.graph.hi_lam", gdir + "hi_lam.py")
+    hip = _load_file("models.step_predictors.graph.hi_lam_parallel", gdir + "hi_lam_parallel.py")
+    _load_file("models.forecasters.base", "neural_lam/models/forecasters/base.py")
+    ar = _load_file("models.forecasters.autoregressive", "neural_lam/models/forecasters/autoregressive.py")
+    ns.StepPredictor, ns.BaseGraphModel, ns.GraphLAM = sp.StepPredictor, gb.BaseGraphModel, glam.GraphLAM
+    ns.BaseHiGraphModel, ns.HiLAM, ns.HiLAMParallel = hier.BaseHiGraphModel, hil.HiLAM, hip.HiLAMParallel
+    ns.ARForecaster = ar.ARForecaster
+    ns.load_graph = gr.load_graph
+    ns.graph_utils = gr
     return ns
 
 

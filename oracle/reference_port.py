@@ -169,7 +169,7 @@ def graph_model_forward(params, graph, cfg, prev_state, prev_prev_state, forcing
     grid_emb = mlp(grid_features, params, p + "grid_embedder", hl)
     g2m_emb = mlp(g["g2m_features"], params, p + "g2m_embedder", hl)
     m2g_emb = mlp(g["m2g_features"], params, p + "m2g_embedder", hl)
-    hierarchical = cfg["model"] != "graph_lam"
+    hierarchical = cfg["model"] != "graph_lam"  # "hi_lam" | "hi_lam_parallel"
     if hierarchical:
         mesh_emb = mlp(g["mesh_static_features"][0], params, p + "mesh_embedders.0", hl)
     else:
@@ -208,8 +208,29 @@ def graph_model_forward(params, graph, cfg, prev_state, prev_prev_state, forcing
                 f"mesh_init_gnns.{l - 1}", g["mesh_up_edge_index"][l - 1], levels[l - 1], levels[l], up[l - 1],
                 gnn_type=up_t,
             )
+        if cfg["model"] == "hi_lam_parallel":
+            # hi_lam_parallel.py:89-122 (offset concatenation) and :186-218: ONE InteractionNet per layer over
+            # all levels / edge sets with per-section MLPs (SplitMLPs)
+            sizes = [t.shape[-2] for t in levels]
+            first = [0]
+            for n in sizes[:-1]:
+                first.append(first[-1] + n)
+            total = [ei + off for ei, off in zip(g["m2m_edge_index"], first)]
+            total += [torch.stack((ei[0] + first[l], ei[1] + first[l + 1])) for l, ei in enumerate(g["mesh_up_edge_index"])]
+            total += [torch.stack((ei[0] + first[l + 1], ei[1] + first[l])) for l, ei in enumerate(g["mesh_down_edge_index"])]
+            sections = [ei.shape[1] for ei in total]
+            tei = torch.cat(total, dim=1)
+            mesh_all = torch.cat(levels, dim=1)
+            edge_all = torch.cat(same + up + down, dim=1)
+            for k in range(cfg["processor_layers"]):
+                mesh_all, edge_all = interaction_net(
+                    params, tei, mesh_all, mesh_all, edge_all, prefix=p + f"processor.module_{k}", hidden_layers=hl,
+                    edge_chunk_sizes=sections, aggr_chunk_sizes=sizes)
+            levels = list(torch.split(mesh_all, sizes, dim=1))
+            parts = torch.split(edge_all, sections, dim=1)
+            same, up, down = list(parts[:L]), list(parts[L:2 * L - 1]), list(parts[2 * L - 1:])
         # hi_lam.py:350-376
-        for k in range(cfg["processor_layers"]):
+        for k in range(cfg["processor_layers"] if cfg["model"] == "hi_lam" else 0):
             # mesh_down_step hi_lam.py:205-236
             levels[-1], same[-1] = gnn(f"mesh_down_same_gnns.{k}.{L - 1}", g["m2m_edge_index"][L - 1], levels[-1], levels[-1], same[-1])
             for l in range(L - 2, -1, -1):
@@ -240,23 +261,43 @@ def graph_model_forward(params, graph, cfg, prev_state, prev_prev_state, forcing
         update_edges=False, gnn_type=cfg.get("m2g_gnn_type", "InteractionNet"),
     )
     net_output = mlp(grid_rep, params, p + "output_map", hl, layer_norm=False)
-    # base.py:339 rescale; :342 / step_predictors/base.py:366 residual
+    pred_std = None
+    if cfg.get("output_std"):
+        # base.py:324-334: mean | raw std halves, softplus on the std half (not rescaled)
+        net_output, std_raw = net_output.chunk(2, dim=-1)
+        pred_std = torch.nn.functional.softplus(std_raw)
+    # base.py:339 rescale; :342 / step_predictors/base.py:366 residual (clamped where limits are configured)
     delta = net_output * g["diff_std"] + g["diff_mean"]
-    return prev_state + delta
+    clamp = cfg.get("clamp")
+    if clamp:
+        new_state = clamped_new_state(delta, prev_state, clamp["names"], clamp["lower"], clamp["upper"],
+                                      clamp["state_mean"].to(dt), clamp["state_std"].to(dt))
+    else:
+        new_state = prev_state + delta
+    if cfg.get("return_std"):
+        return new_state, pred_std
+    return new_state
 
 
 def ar_rollout(params, graph, cfg, init_states, forcing_features, boundary_states, prefix="predictor"):
-    """``ARForecaster.forward`` (models/forecasters/autoregressive.py:113-149)."""
+    """``ARForecaster.forward`` (models/forecasters/autoregressive.py:113-149).  Returns the stacked prediction, or
+    ``(prediction, pred_std)`` when ``cfg["return_std"]`` (std None for predictors without one, :142-148)."""
     dt = init_states.dtype
     bm = graph["boundary_mask"].to(dt)
     im = 1.0 - bm
     prev_prev, prev = init_states[:, 0], init_states[:, 1]
-    preds = []
+    preds, stds = [], []
     for i in range(forcing_features.shape[1]):
         pred = graph_model_forward(params, graph, cfg, prev, prev_prev, forcing_features[:, i], prefix=prefix)
+        if cfg.get("return_std"):
+            pred, std = pred
+            if std is not None:
+                stds.append(std)
         new = bm * boundary_states[:, i] + im * pred  # autoregressive.py:128-131
         preds.append(new)
         prev_prev, prev = prev, new
+    if cfg.get("return_std"):
+        return torch.stack(preds, dim=1), (torch.stack(stds, dim=1) if stds else None)
     return torch.stack(preds, dim=1)
 
 
