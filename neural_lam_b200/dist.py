@@ -163,7 +163,11 @@ class PartitionedGraphLAM(models.GraphLAM):
         ds.num_state_vars = datastore.num_state_vars
         ds.state_diff_mean, ds.state_diff_std = datastore.state_diff_mean, datastore.state_diff_std
         ds.grid_input_dim = datastore.grid_input_dim
+        ds.state_var_names, ds.state_mean, ds.state_std = datastore.state_var_names, datastore.state_mean, datastore.state_std
         super().__init__(ds, local, **kwargs)
+        if self.output_std or self.clamps_output:
+            raise NotImplementedError("PartitionedGraphLAM: output_std / output clamping are not supported on the "
+                                      "partitioned inference path")
         self.rank, self.world, self.group = rank, world, group
         self.grid_bounds, self.mesh_bounds = grid_bounds, mesh_bounds
         self.plans = plans

@@ -136,6 +136,23 @@ class InteractionNet(nn.Module):
             self.aggr_mlp = SplitMLPs([make_mlp(aggr_recipe) for _ in aggr_chunk_sizes], aggr_chunk_sizes)
         self.update_edges = update_edges
 
+    # graph handles (ctypes pointers into the library) are per-process device resources: copies and pickles of
+    # the module drop them and rebuild lazily (copy.deepcopy for EMA / SWA, torch.save of whole modules)
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_graphs"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_graphs" else copy.deepcopy(v, memo)
+        return new
+
     # ------------------------------------------------------------------ helpers
     @property
     def num_edges(self):

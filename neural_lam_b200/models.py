@@ -164,7 +164,13 @@ class BaseGraphModel(StepPredictor):
 
     # -- static (input independent) embeddings ----------------------------------------------
     def _static_param_version(self):
-        return tuple(p._version for p in self._static_params())
+        # (version counter, storage address): ``p.data = new`` (EMA-style weight swaps) changes the address without
+        # bumping the counter, in-place optimiser steps bump the counter without changing the address
+        return tuple((p._version, p.data_ptr()) for p in self._static_params())
+
+    def invalidate_static_cache(self):
+        """Drop the cached input-independent embeddings (they are rebuilt on the next no-grad forward)."""
+        self._static_cache = None
 
     def _static_params(self):
         raise NotImplementedError
@@ -510,8 +516,22 @@ class ARForecaster(nn.Module):
                 self._one_step(bufs, k)
             graphs.append(g)
         self._graph = (batch_size, graphs, bufs)
+        # the graphs hold the cached static embeddings and every weight BY ADDRESS: remember what they were captured
+        # against so that a later weight update / load_state_dict / .to() triggers a re-capture instead of a stale replay
+        self._graph_key = self._capture_key(batch_size)
+        self._graph_static = p._static_cache  # keeps the captured embedding tensors alive while the graphs exist
         self._phase = 0
         return bufs
+
+    def _capture_key(self, batch_size):
+        p = self.predictor
+        return (batch_size, self.boundary_mask.device, p._static_param_version(),
+                tuple(q.data_ptr() for q in p.parameters()))
+
+    def _ensure_captured(self, batch_size):
+        if self._graph is None or getattr(self, "_graph_key", None) != self._capture_key(batch_size):
+            self._io = None
+            self.capture(batch_size)
 
     def _one_step(self, bufs, k):
         st = bufs["state"]
@@ -538,8 +558,7 @@ class ARForecaster(nn.Module):
     def rollout_graphed(self, init_states, forcing_features, boundary_states):
         """Same result as ``forward`` (no std), replaying the captured step graphs."""
         B, T = forcing_features.shape[0], forcing_features.shape[1]
-        if self._graph is None or self._graph[0] != B:
-            self.capture(B)
+        self._ensure_captured(B)
         _, _, bufs = self._graph
         out = torch.empty(B, T, *init_states.shape[2:], device=init_states.device)
         self.set_state(init_states[:, 0], init_states[:, 1])
@@ -559,8 +578,7 @@ class ARForecaster(nn.Module):
         (B,T,G,d) prediction on the host (``out`` if given)."""
         B, T = forcing_features.shape[0], forcing_features.shape[1]
         dev = self.boundary_mask.device
-        if self._graph is None or self._graph[0] != B:
-            self.capture(B)
+        self._ensure_captured(B)
         _, _, bufs = self._graph
         if out is None:
             out = torch.empty(B, T, *init_states.shape[2:], dtype=torch.float32, pin_memory=True)

@@ -311,6 +311,9 @@ def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None)
     net_out, prev = net_out.contiguous(), prev.contiguous()
     _require_cuda(net_out, prev, diff_std, diff_mean, boundary, bmask)
     B, G, D = net_out.shape
+    if prev.shape != net_out.shape or diff_std.numel() != D or diff_mean.numel() != D:
+        raise ValueError(f"step_epilogue: net_out {tuple(net_out.shape)}, prev {tuple(prev.shape)}, diff statistics "
+                         f"{diff_std.numel()}/{diff_mean.numel()} disagree")
     if out is None:
         out = torch.empty_like(net_out)
     assert out.is_contiguous() and out.shape == net_out.shape

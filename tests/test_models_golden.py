@@ -44,9 +44,9 @@ def test_tensor_core_kernels_match_reference_golden(case):
     per_step = [float(err[:, t].max()) for t in range(err.shape[1])]
     print(f"{case.name}: TF32 path max |err| vs reference golden per AR step: {per_step}")
     assert max(per_step) < 3e-2, per_step
-    # CUDA-graph replay and the host-buffer API give the eager result bit for bit
+    # CUDA-graph replay and the host-buffer API give the eager result
     with torch.no_grad():
         graphed = fc.rollout_graphed(case.init.cuda(), case.forcing.cuda(), case.boundary.cuda()).cpu()
         host = fc.rollout_from_host(case.init.pin_memory(), case.forcing.pin_memory(), case.boundary.pin_memory())
-    torch.testing.assert_close(graphed, pred, rtol=0, atol=0)
-    torch.testing.assert_close(host, pred, rtol=0, atol=0)
+    torch.testing.assert_close(graphed, pred, rtol=1e-6, atol=1e-6)  # fused boundary mix: FMA contraction only
+    torch.testing.assert_close(host, graphed, rtol=0, atol=0)
