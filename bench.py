@@ -17,7 +17,13 @@ value = forecast-steps/sec = N*B*K / t.
                   algorithmic bytes / CUDA-event time with L2 flushed between
                   iterations, against MEASURED_PEAKS.json hbm_gbs.
   * `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference op sequence
-                  (oracle/reference_port.py) on the host cores, bounded sample.
+                  (oracle/reference_port.py) on the host cores, bounded sample, SAME batch as our arm.
+  * `ref_cuda`  : the reference op sequence (index_select + cat + Linear/SiLU/LayerNorm + index_add_, what
+                  PyG 2.3.1 without torch-scatter executes) moved to the GPU with TF32 matmuls on, as the
+                  reference configures itself (train_model.py:484-488), same batch, CUDA-event timed.
+  * `kernels`   : per-launch table of one eager step (library-side CUDA events around every launch):
+                  kernel, µs, algorithmic bytes, GB/s, fraction of the measured HBM peak.
+  * `parity`    : our step vs the fp64 oracle on the same inputs at the workload's real size (B=2, 1 step).
 N>1: one process per GPU (torchrun), independent replicas (the reference's only parallelism is
 DDP replicas, README.md:486-514): weak scaling, no data-path collective.
 """
@@ -142,13 +148,13 @@ def time_cpu_reference(params, g, cfg, G, steps, warmup, B=1):
     ncpu = os.cpu_count() or 1
     init, forc, bnd = synth_inputs(B, max(1, steps + warmup), G)
     # "all the host threads it can use": torch's intra-op pool does not scale to 100+ threads on
-    # these small ops, so probe a few pool sizes with one step each and keep the fastest
+    # these small ops, so probe a few pool sizes with one B=1 step each and keep the fastest
     best = (None, 1e30)
     with torch.no_grad():
         for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
             torch.set_num_threads(nt)
             t0 = time.perf_counter()
-            rp.ar_rollout(params, g, cfg, init, forc[:, :1], bnd[:, :1])
+            rp.ar_rollout(params, g, cfg, init[:1], forc[:1, :1], bnd[:1, :1])
             dt = time.perf_counter() - t0
             if dt < best[1]:
                 best = (nt, dt)
@@ -196,6 +202,83 @@ def roofline_m2m(model, B, device, iters=20):
     mean_ms = sum(ms) / len(ms)
     nbytes = algorithmic_bytes_inet(B, Nm, Nm, E, H, True, True)
     return nbytes, mean_ms, ms[len(ms) // 2]
+
+
+
+def kernel_table(fc, bufs, peak):
+    """One EAGER forecast step with the library's per-launch profile on: [{kernel, us, bytes, gbs, frac}] in launch
+    order.  The step's tensors (hundreds of MB at the bench batch) stream through the 126 MB L2 exactly as in the
+    replayed step; the launches are the same ones the CUDA graph holds."""
+    import ctypes
+
+    from neural_lam_b200 import _lib
+
+    L = _lib.lib()
+    with torch.no_grad():
+        fc._one_step(bufs, 0)
+        torch.cuda.synchronize()
+        L.nlam_profile_enable(1)
+        fc._one_step(bufs, 0)
+        torch.cuda.synchronize()
+        n = L.nlam_profile_count()
+        rows = []
+        name = ctypes.create_string_buffer(96)
+        ms, nb = ctypes.c_float(), ctypes.c_double()
+        for i in range(n):
+            _lib.check(L.nlam_profile_get(i, name, 96, ctypes.byref(ms), ctypes.byref(nb)))
+            us = ms.value * 1e3
+            gbs = nb.value / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            rows.append({"kernel": name.value.decode(), "us": round(us, 1), "bytes": int(nb.value),
+                         "gbs": round(gbs, 1), "frac": round(gbs / peak, 3)})
+        L.nlam_profile_enable(0)
+    return rows
+
+
+def time_ref_cuda(model, fc, device, B, steps, warmup):
+    """The reference op sequence on the GPU (the reference's "PyG/CUDA path"): oracle/reference_port.ar_rollout —
+    index_select gathers, cat, nn.Linear-equivalent matmuls, SiLU, LayerNorm, index_add_ scatter — on CUDA tensors
+    with TF32 matmuls enabled as the reference does (train_model.py:484-488).  Returns (steps/s, ms per step)."""
+    from oracle import reference_port as rp
+
+    params, g, cfg = oracle_setup(model, fc)
+    params = {k: v.to(device) for k, v in params.items()}
+    g = {k: v.to(device) for k, v in g.items()}
+    G = model.num_grid_nodes
+    init, forc, bnd = (t.to(device) for t in synth_inputs(B, steps + warmup, G, seed=321))
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        with torch.no_grad():
+            rp.ar_rollout(params, g, cfg, init, forc[:, :warmup], bnd[:, :warmup])
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rp.ar_rollout(params, g, cfg, init, forc[:, warmup:], bnd[:, warmup:])
+            e1.record()
+            torch.cuda.synchronize(device)
+    finally:
+        torch.set_float32_matmul_precision(old)
+    ms = e0.elapsed_time(e1) / steps
+    return B / (ms * 1e-3), ms
+
+
+def parity_check(model, fc, device, B=2):
+    """Our step vs the fp64 CPU oracle at the workload's real size: max abs / max rel error of one forecast step,
+    next to the error of the reference's own GPU configuration (fp32 oracle with TF32-rounded matmul operands)."""
+    from oracle import reference_port as rp
+
+    params, g, cfg = oracle_setup(model, fc)
+    G = model.num_grid_nodes
+    init, forc, bnd = synth_inputs(B, 1, G, seed=777)
+    with torch.no_grad():
+        want = rp.ar_rollout({k: v.double() for k, v in params.items()}, g, cfg, init.double(), forc.double(), bnd.double())
+        with rp.tf32_matmul():
+            ref = rp.ar_rollout(params, g, cfg, init, forc, bnd)
+        got = fc.rollout_graphed(init.to(device), forc.to(device), bnd.to(device)).cpu().double()
+    err = (got - want).abs()
+    return {"max_abs": err.max().item(), "max_rel": (err / want.abs().clamp(min=1.0)).max().item(),
+            "reference_tf32_max_abs": (ref.double() - want).abs().max().item(),
+            "what": f"1 forecast step, B={B}, real-size workload, vs fp64 oracle (rel = |err|/max(|x|,1))"}
 
 
 def run_ours(args):
@@ -286,20 +369,31 @@ def run_ours(args):
         with torch.no_grad():
             nbytes, mean_ms, med_ms = roofline_m2m(model, B, device)
         achieved = nbytes / (mean_ms * 1e-3) / 1e9
+        # DRAM traffic of the roofline kernel from an `ncu --set full` capture AT THIS BATCH (profiles/traffic.json:
+        # {"m2m_layer_dram_bytes": {"<B>": bytes}}); null when no capture exists for the batch that was run
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             try:
-                traffic = json.load(open(tp)).get("m2m_layer_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("m2m_layer_dram_bytes", {}).get(str(B))
             except Exception:
                 traffic = None
+        kernels = kernel_table(fc, bufs, peak)
+        parity = None if args.no_parity else parity_check(model, fc, device)
+        ref_cuda = None
+        if not args.no_ref_cuda:
+            v, ms = time_ref_cuda(model, fc, device, B, steps=min(K, 10), warmup=2)
+            ref_cuda = {"value": v, "unit": "forecast-steps/s", "ms_per_step": ms, "batch_per_gpu": B,
+                        "what": "reference op sequence (oracle port of gnn_layers.py + PyG 2.3.1 gather/scatter_add + "
+                                "graph/base.py) on this GPU, torch fp32 with TF32 matmuls (train_model.py:484-488), eager"}
         cpu = None
         if world >= 1 and not args.no_cpu_baseline:
             params, g, cfg = oracle_setup(model, fc)
-            v, sec, cores = time_cpu_reference(params, g, cfg, G, steps=args.cpu_steps, warmup=1, B=1)
+            n_cpu = max(1, min(args.cpu_steps, 2))
+            v, sec, cores = time_cpu_reference(params, g, cfg, G, steps=n_cpu, warmup=1, B=B)
             cpu = {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
-                   "sample": f"B=1, {args.cpu_steps} AR steps of the same GraphLAM config after 1 warm-up "
-                             f"({sec:.3f} s/step, torch CPU {torch.get_num_threads()} threads)"}
+                   "sample": f"B={B} (same batch as the GPU arm), {n_cpu} AR steps of the same GraphLAM config after 1 "
+                             f"warm-up ({sec:.3f} s per step of {B} forecasts, torch CPU {torch.get_num_threads()} threads)"}
         h2d = B * G * (D_FORCING + D_STATE) * 4
         d2h = B * G * D_STATE * 4
         line = {
@@ -328,7 +422,12 @@ def run_ours(args):
                          "traffic": traffic, "algorithmic_bytes": nbytes, "ms_mean": mean_ms, "ms_median": med_ms,
                          "peak_source": peak_src, "l2_flushed": True},
             "cpu_baseline": cpu,
+            "ref_cuda": ref_cuda,
+            "parity": parity,
+            "kernels": kernels,
         }
+        if ref_cuda:
+            line["ref_cuda"]["speedup_device_resident"] = line["value"] / world / ref_cuda["value"]
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -346,8 +445,10 @@ def run_reference(args):
     spec, ds, model, fc = build_model(None)
     params, g, cfg = oracle_setup(model, fc)
     K, W = args.steps, args.warmup
-    k = max(1, min(K, args.cpu_steps))
-    v, sec, cores = time_cpu_reference(params, g, cfg, model.num_grid_nodes, steps=k, warmup=min(W, 1), B=1)
+    B = args.batch
+    # each step = one forecast step of the SAME batch as our arm (B forecasts); bounded sample of the K steps
+    k = max(1, min(K, args.cpu_steps, 3))
+    v, sec, cores = time_cpu_reference(params, g, cfg, model.num_grid_nodes, steps=k, warmup=min(W, 1), B=B)
     line = {
         "impl": "reference",
         "metric": "forecast-steps/sec (268x238 grid, hidden=64)",
@@ -355,9 +456,10 @@ def run_reference(args):
         "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers "
-                               "(BASELINE.json configs[1])", "batch_per_gpu": 1},
+                               "(BASELINE.json configs[1])", "batch_per_gpu": B, "global_batch": B,
+                   "math": "f32 (torch CPU)", "parallelism": "host cores of one box"},
         "cpu_baseline": {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"each step = one B=1 forecast step on the host cores; {k} timed steps "
+                         "sample": f"each step = one forecast step of B={B} forecasts on the host cores; {k} timed steps "
                                    f"(bounded from --steps {K})"},
         "e2e": {"value": v, "unit": "forecast-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -374,6 +476,8 @@ def main():
     ap.add_argument("--math", default="auto", choices=["auto", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,15 @@ const char* nlam_build_info(void);
  * launch recorded into a CUDA graph during stream capture counts once) */
 int64_t nlam_launch_count(void);
 
+/* Per-launch profile (measurement aid for bench.py's per-kernel roofline table): while enabled, every kernel
+ * launch of the library is bracketed by CUDA events on its stream.  nlam_profile_enable(1) clears the record and
+ * starts collecting, (0) stops; nlam_profile_get returns launch i's kernel name, device time (ms; waits for the
+ * launch to finish) and its algorithmic bytes (distinct input bytes + output bytes).  Not for use inside a CUDA
+ * stream capture. */
+void nlam_profile_enable(int on);
+int nlam_profile_count(void);
+int nlam_profile_get(int i, char* name, int name_cap, float* ms, double* bytes);
+
 /* Build the device CSR of one edge set.  edge_index is a HOST pointer to the (2,E) int64
  * array the reference passes to InteractionNet (row 0 senders, row 1 receivers, both
  * zero-based in their own node set).  num_rec = max(receiver)+1 as the reference infers it

@@ -59,6 +59,10 @@ SYMBOLS = {
     "nlam_last_error": (ctypes.c_char_p, []),
     "nlam_build_info": (ctypes.c_char_p, []),
     "nlam_launch_count": (ctypes.c_int64, []),
+    "nlam_profile_enable": (None, [ctypes.c_int]),
+    "nlam_profile_count": (ctypes.c_int, []),
+    "nlam_profile_get": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.POINTER(ctypes.c_double)]),
     "nlam_graph_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "nlam_graph_destroy": (None, [ctypes.c_void_p]),
     "nlam_graph_num_edges": (ctypes.c_int64, [ctypes.c_void_p]),

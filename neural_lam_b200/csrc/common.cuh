@@ -36,6 +36,17 @@ const char* get_error();
 void count_launch(int n = 1);
 int64_t launch_count();
 
+// Per-launch profile (nlam_profile_*): when enabled, every kernel launch of the library is bracketed by CUDA events
+// on its stream and recorded with its name and its ALGORITHMIC bytes (distinct input bytes + output bytes of that
+// launch) — the per-kernel roofline table of bench.py.  Off by default; never enable it inside a stream capture.
+void prof_begin(const char* name, cudaStream_t st, double bytes);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  ProfScope(const char* name, cudaStream_t s, double bytes) : st(s) { prof_begin(name, s, bytes); }
+  ~ProfScope() { prof_end(st); }
+};
+
 constexpr int kTileEdges = 128;  // rows of one tensor-core edge tile (UMMA M)
 
 struct StepEpilogue {  // fused forecast-step epilogue of a narrow-output row MLP (see TcParams::ep_*)
@@ -68,6 +79,12 @@ bool tc_ell_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, co
 int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
                 int64_t rec_bs, const float* edge, int64_t edge_bs, float* aggr_out, int B, int flags,
                 cudaStream_t stream, float* ws);
+// algorithmic bytes of the edge work of one InteractionNet call (SURVEY.md 8d without the node update)
+inline double edge_algorithmic_bytes(const NlamGraph* g, int B, int64_t send_bs, int64_t rec_bs, int64_t edge_bs, bool has_out,
+                                     int H);
+// algorithmic bytes of a row-MLP launch: every distinct source / residual / epilogue input once, the output once
+double rowmlp_algorithmic_bytes(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                                const NlamRowSrc* res2, int64_t n_rows, int B, bool out2, const StepEpilogue* ep);
 }  // namespace nlam
 
 // Receiver-sorted CSR of one edge set + sender CSR + tensor-core tile table.
@@ -108,6 +125,14 @@ struct NlamGraph {
 };
 
 namespace nlam {
+inline double edge_algorithmic_bytes(const NlamGraph* g, int B, int64_t send_bs, int64_t rec_bs, int64_t edge_bs, bool has_out,
+                                     int H) {
+  const double row = 4.0 * H;
+  const int Bs = (send_bs != 0 && B > 1) ? B : 1, Br = (rec_bs != 0 && B > 1) ? B : 1, Be = (edge_bs != 0 && B > 1) ? B : 1;
+  return row * ((double)g->n_edges * Be + (double)g->n_send * Bs + (double)g->n_rec * Br + (double)g->n_rec * B +
+                (has_out ? (double)g->n_edges * B : 0.0)) +
+         4.0 * g->n_edges + 4.0 * (g->n_rec + 1) + 4.0 * (4.0 * H * H + 5.0 * H);
+}
 
 // simt.cu
 int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,

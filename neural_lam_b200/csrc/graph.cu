@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <numeric>
 
 #include "common.cuh"
@@ -21,7 +22,90 @@ const char* get_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+struct ProfRec {
+  const char* name;
+  double bytes;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static bool g_prof_on = false;
+
+void prof_begin(const char* name, cudaStream_t st, double bytes) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{name, bytes, nullptr, nullptr};
+  if (!g_prof_pool.empty()) {
+    r.e0 = g_prof_pool.back().first;
+    r.e1 = g_prof_pool.back().second;
+    g_prof_pool.pop_back();
+  } else if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, st);
+}
+
+double rowmlp_algorithmic_bytes(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
+                                const NlamRowSrc* res2, int64_t n_rows, int B, bool out2, const StepEpilogue* ep) {
+  double b = 0;
+  const void* seen[8];
+  int n_seen = 0;
+  auto add = [&](const NlamRowSrc* r) {
+    if (!r || !r->ptr) return;
+    for (int i = 0; i < n_seen; ++i)
+      if (seen[i] == r->ptr) return;
+    if (n_seen < 8) seen[n_seen++] = r->ptr;
+    // gathered sources are counted per output row (upper bound of the distinct rows read)
+    b += 4.0 * (double)n_rows * r->dim * ((r->bstride != 0 && B > 1) ? B : 1);
+    if (r->idx) b += 4.0 * (double)n_rows;
+  };
+  for (int s = 0; s < n_src; ++s) add(&srcs[s]);
+  add(res);
+  add(res2);
+  const int nout = mlp->out_dim[mlp->n_linear - 1];
+  b += 4.0 * (double)n_rows * nout * B * (out2 ? 2 : 1);
+  if (ep) {
+    b += 4.0 * (double)n_rows * nout * B;                     // previous state
+    if (ep->boundary) b += 4.0 * (double)n_rows * nout * B + 4.0 * (double)n_rows;  // boundary state + mask
+  }
+  double w = mlp->in_dim;
+  for (int l = 0; l < mlp->n_linear; ++l) {
+    b += 4.0 * (w * mlp->out_dim[l] + mlp->out_dim[l]);
+    w = mlp->out_dim[l];
+  }
+  return b;
+}
 }  // namespace nlam
+
+extern "C" void nlam_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(nlam::g_prof_mu);
+  for (auto& r : nlam::g_prof) nlam::g_prof_pool.push_back({r.e0, r.e1});
+  nlam::g_prof.clear();
+  nlam::g_prof_on = on != 0;
+}
+extern "C" int nlam_profile_count(void) {
+  std::lock_guard<std::mutex> lk(nlam::g_prof_mu);
+  return (int)nlam::g_prof.size();
+}
+extern "C" int nlam_profile_get(int i, char* name, int name_cap, float* ms, double* bytes) {
+  std::lock_guard<std::mutex> lk(nlam::g_prof_mu);
+  NLAM_REQUIRE(i >= 0 && i < (int)nlam::g_prof.size() && name && ms && bytes && name_cap > 0, NLAM_E_INVALID,
+               "nlam_profile_get: bad index / null argument");
+  const nlam::ProfRec& r = nlam::g_prof[i];
+  NLAM_CUDA_OK(cudaEventSynchronize(r.e1));
+  NLAM_CUDA_OK(cudaEventElapsedTime(ms, r.e0, r.e1));
+  snprintf(name, name_cap, "%s", r.name);
+  *bytes = r.bytes;
+  return NLAM_OK;
+}
 
 using namespace nlam;
 

@@ -275,7 +275,10 @@ int rowmlp_simt(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
   NLAM_CUDA_OK(cudaFuncSetAttribute(rowmlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = std::max<int>(1, (int)((220 * 1024) / (smem + 1024)));
   int grid = (int)std::min<long long>(n_work, (long long)148 * std::min(occ, 4));
-  rowmlp_simt_kernel<<<grid, NT, smem, stream>>>(p);
+  {
+    ProfScope ps("rowmlp_simt_kernel", stream, rowmlp_algorithmic_bytes(mlp, srcs, n_src, res, res2, n_rows, B, out2 != nullptr, nullptr));
+    rowmlp_simt_kernel<<<grid, NT, smem, stream>>>(p);
+  }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
@@ -381,6 +384,7 @@ extern "C" int nlam_segment_sum(const int32_t* ptr, const int32_t* order, int64_
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = (H % 4 == 0) && (x_bstride % 4 == 0) && (out_bstride % 4 == 0) &&
              ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  ProfScope ps("segment_sum_kernel", st, 4.0 * H * B * (double)n_seg * 2 + 4.0 * n_seg);  // + the rows it reads (unknown here)
   if (vec) {
     long long total = (long long)B * n_seg * (H / 4);
     segment_sum_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(ptr, order, n_seg, x, x_bstride, out, out_bstride, B, H, mean);
@@ -401,6 +405,7 @@ extern "C" int nlam_gather_rows(const float* x, int64_t x_bstride, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = (H % 4 == 0) && (x_bstride % 4 == 0) && (out_bstride % 4 == 0) &&
              ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  ProfScope ps("gather_rows_kernel", st, 4.0 * H * B * (double)n_rows * 2 + 4.0 * n_rows);
   if (vec) {
     long long total = (long long)B * n_rows * (H / 4);
     gather_rows_kernel<4><<<grid_for(total, 256), 256, 0, st>>>(x, x_bstride, idx, n_rows, out, out_bstride, B, H, deg_ptr);
@@ -420,8 +425,11 @@ extern "C" int nlam_step_epilogue(const float* net_out, const float* prev, const
   NLAM_REQUIRE((boundary == nullptr) || bmask, NLAM_E_INVALID, "step_epilogue: boundary without mask");
   long long total = B * G * D;
   if (total == 0) return NLAM_OK;
-  step_epilogue_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(net_out, prev, boundary, bmask, diff_std,
-                                                                               diff_mean, new_state, B, G, D);
+  {
+    ProfScope ps("step_epilogue_kernel", (cudaStream_t)stream, 4.0 * total * (boundary ? 4 : 3));
+    step_epilogue_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(net_out, prev, boundary, bmask, diff_std,
+                                                                                 diff_mean, new_state, B, G, D);
+  }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;

@@ -794,7 +794,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
 
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2,
-                  const CUtensorMap& om, const TcParams& p, cudaStream_t st, const CUtensorMap* g0 = nullptr,
+                  const CUtensorMap& om, const TcParams& p, cudaStream_t st, double bytes, const CUtensorMap* g0 = nullptr,
                   const CUtensorMap* g1 = nullptr) {
   static unsigned attr_mask = 0;  // per device
   int dev = 0;
@@ -815,7 +815,10 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     pp.dbg = dbg_buf;
   }
-  tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, om, g0 ? *g0 : om, g1 ? *g1 : om, pp);
+  {
+    ProfScope ps(p.mode_edge ? "tc_mlp_kernel(edge)" : "tc_mlp_kernel(row)", st, bytes);
+    tc_mlp_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a0, a1, w1, w2, om, g0 ? *g0 : om, g1 ? *g1 : om, pp);
+  }
   if (dbg_on) {
     long long h[256];
     NLAM_CUDA_OK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -938,7 +941,7 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
     rc = make_map(&om, out, 64, (uint64_t)n_rows, (uint64_t)B, 64, (uint64_t)n_rows * 64, BM, true);
     if (rc) return rc;
   }
-  return launch(a0, a1, w1, w2, om, p, st);
+  return launch(a0, a1, w1, w2, om, p, st, rowmlp_algorithmic_bytes(mlp, srcs, n_src, res, nullptr, n_rows, B, false, ep));
 }
 
 bool tc_edge_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags) {
@@ -1015,9 +1018,9 @@ int tc_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int6
     p.use_g4 = 1;
     p.g4_rows[0] = (send_bs == 0 || B == 1) ? 0 : (int)send_rows;
     p.g4_rows[1] = (rec_bs == 0 || B == 1) ? 0 : (int)nr;
-    return launch(a0, a1, w1, w2, om, p, st, &g0, &g1);
+    return launch(a0, a1, w1, w2, om, p, st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64), &g0, &g1);
   }
-  return launch(a0, a1, w1, w2, om, p, st);
+  return launch(a0, a1, w1, w2, om, p, st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
 }
 
 }  // namespace nlam

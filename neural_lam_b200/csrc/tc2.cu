@@ -724,7 +724,12 @@ int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st) {
     attr_mask |= 1u << (dev & 31);
   }
   const int grid = (int)std::min<long long>(p.n_work, num_sms());
-  tc_rowlinear_kernel<<<grid, rl::THREADS, rl::SMEM, st>>>(mx[0], mw[0], mo[0], mx[1], mw[1], mo[1], p);
+  {
+    double bytes = 0;
+    for (int i = 0; i < n_prob; ++i) bytes += 2.0 * 256.0 * (double)pr[i].n_rows * pr[i].B_eff + 4.0 * (64 * 64 + 64);
+    ProfScope ps("tc_rowlinear_kernel", st, bytes);
+    tc_rowlinear_kernel<<<grid, rl::THREADS, rl::SMEM, st>>>(mx[0], mw[0], mo[0], mx[1], mw[1], mo[1], p);
+  }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
@@ -846,7 +851,10 @@ int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-  tc_edge2_kernel<<<grid, e2::THREADS, e2::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
+  {
+    ProfScope ps("tc_edge2_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
+    tc_edge2_kernel<<<grid, e2::THREADS, e2::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
+  }
   count_launch();
   if (dbg_on) {
     long long h[256];

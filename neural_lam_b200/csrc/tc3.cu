@@ -1033,8 +1033,10 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     static int pf = -1;
     if (pf < 0) pf = getenv("NLAM_ELL_NO_PREFETCH") ? 0 : 1;
     q.prefetch = pf;
+    ProfScope ps("tc_ell_window_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, false, 64));
     tc_ell_window_kernel<<<grid, e4::THREADS, e4::SMEM, st>>>(me, mrec, mw1, mw2, mps, mo, q);
   } else {
+    ProfScope ps("tc_ell_edge_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, false, 64));
     tc_ell_edge_kernel<<<grid, e3::THREADS, e3::SMEM, st>>>(me, mrec, mw1, mw2, mps, p);
   }
   count_launch();

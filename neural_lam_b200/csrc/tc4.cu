@@ -697,7 +697,11 @@ int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-  tc_rowmlp64_kernel<<<grid, r4::THREADS, r4::SMEM, st>>>(a[0], a[1], w1, w2, om, p);
+  {
+    ProfScope ps(ep ? "tc_rowmlp64_kernel(step)" : (kind == 2 ? "tc_rowmlp64_kernel(narrow-in)" : "tc_rowmlp64_kernel"), st,
+                 rowmlp_algorithmic_bytes(mlp, srcs, n_src, res, nullptr, n_rows, B, false, ep));
+    tc_rowmlp64_kernel<<<grid, r4::THREADS, r4::SMEM, st>>>(a[0], a[1], w1, w2, om, p);
+  }
   count_launch();
   if (dbg_on) {
     long long h[256];

@@ -590,7 +590,11 @@ int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-  tc_edge3_kernel<<<grid, e5::THREADS, e5::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
+  {
+    // the node-side terms arrive as projections (same row counts as the raw node rows)
+    ProfScope ps("tc_edge3_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
+    tc_edge3_kernel<<<grid, e5::THREADS, e5::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
+  }
   count_launch();
   if (dbg_on) {
     long long h[256];

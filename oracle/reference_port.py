@@ -9,9 +9,36 @@ equivalent") and fp64 ("ground truth").  All parameters come in as a flat
 Each function cites the reference code it follows (paths relative to
 ``/root/reference``).
 """
+import contextlib
 import math
 
 import torch
+
+# --------------------------------------------------------------------------------------------------
+# The reference's GPU configuration: ``torch.set_float32_matmul_precision("high")`` whenever CUDA is
+# available (train_model.py:484-488) = TF32 tensor-core matmuls: both operands rounded to TF32 (10
+# explicit mantissa bits), products accumulated in fp32.  ``tf32_matmul()`` makes ``mlp`` emulate that on
+# the CPU, so that "the error of the reference's own GPU configuration" is a number the tests can state
+# without a GPU run of the reference.
+# --------------------------------------------------------------------------------------------------
+_TF32 = False
+
+
+@contextlib.contextmanager
+def tf32_matmul(enabled=True):
+    global _TF32
+    old, _TF32 = _TF32, bool(enabled)
+    try:
+        yield
+    finally:
+        _TF32 = old
+
+
+def round_tf32(x):
+    """fp32 -> nearest TF32 value (round half away from zero on the 13 dropped mantissa bits), kept in fp32."""
+    assert x.dtype == torch.float32
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 # ---------------------------------------------------------------------------
@@ -29,7 +56,10 @@ def mlp(x, params, prefix, hidden_layers=1, layer_norm=True, eps=1e-5):
     for k in range(hidden_layers + 1):
         w = params[f"{prefix}.{2 * k}.weight"].to(h.dtype)
         b = params[f"{prefix}.{2 * k}.bias"].to(h.dtype)
-        h = h @ w.t() + b
+        if _TF32 and h.dtype == torch.float32:
+            h = round_tf32(h) @ round_tf32(w).t() + b
+        else:
+            h = h @ w.t() + b
         if k != hidden_layers:
             h = h * torch.sigmoid(h)  # SiLU
     if layer_norm:
