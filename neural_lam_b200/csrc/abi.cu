@@ -88,6 +88,12 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
       rc = tc_edge3_enabled()
                ? tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, proj)
                : tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows, proj);
+    } else if (tc_edge_bcast_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs, B, edge_out != nullptr) &&
+               workspace && ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
+      // batch-broadcast edge features, large sender set, no edge update (grid -> mesh): tile-major kernel with the
+      // edge term resident in TMEM and raw sender rows gathered (tc6.cu)
+      rc = tc_edge_bcast(g, edge_mlp, send, send_bs, rec, rec_bs, edge, aggr, B, flags, st,
+                         (float*)((char*)workspace + msg_bytes + agg_bytes));
     } else {
       rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
     }

@@ -63,6 +63,24 @@ size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_ma
 int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, int64_t send_rows, float* ws);
+// tc2.cu: out = x · wsliceᵀ (+ bias) for 64-wide rows; wslice = 64 columns of a row-major weight with row pitch ldw
+struct RowLinProblem {
+  const float* x;
+  int64_t x_bs;
+  int64_t n_rows;
+  int B_eff;
+  const float* wslice;
+  int ldw;
+  const float* bias;
+  float* out;
+};
+int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st);
+// tc6.cu: batch-broadcast edge features, no edge update, raw sender rows gathered (grid -> mesh)
+bool tc_edge_bcast_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
+                             const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, int B, bool has_edge_out);
+size_t tc_edge_bcast_workspace_floats(const NlamGraph* g, int B, int64_t rec_bs);
+int tc_edge_bcast(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                  int64_t rec_bs, const float* edge, float* aggr_out, int B, int flags, cudaStream_t st, float* ws);
 // tc5.cu
 bool tc_edge3_enabled();
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,

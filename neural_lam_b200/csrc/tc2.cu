@@ -674,17 +674,6 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------ host
-struct RowLinProblem {
-  const float* x;
-  int64_t x_bs;
-  int64_t n_rows;
-  int B_eff;
-  const float* wslice;
-  int ldw;
-  const float* bias;
-  float* out;
-};
-
 // one launch for 1 or 2 projection problems
 int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st) {
   NLAM_REQUIRE(n_prob == 1 || n_prob == 2, NLAM_E_INVALID, "rowlinear_multi: 1 or 2 problems");

@@ -10,6 +10,31 @@ from . import _lib
 from ._lib import NlamMlp, NlamRowSrc
 
 
+class profile_launches:
+    """``with profile_launches() as prof: ...`` — collects (kernel name, µs, algorithmic bytes) of every kernel the
+    library launches inside the block (``nlam_profile_*``: CUDA events around each launch; eager mode only, not inside
+    a CUDA-graph capture).  ``prof.rows`` is filled on exit."""
+
+    def __enter__(self):
+        self.rows = []
+        _lib.lib().nlam_profile_enable(1)
+        return self
+
+    def __exit__(self, *exc):
+        L = _lib.lib()
+        torch.cuda.synchronize()
+        name = ctypes.create_string_buffer(96)
+        ms, nb = ctypes.c_float(), ctypes.c_double()
+        for i in range(L.nlam_profile_count()):
+            _lib.check(L.nlam_profile_get(i, name, 96, ctypes.byref(ms), ctypes.byref(nb)))
+            self.rows.append((name.value.decode(), ms.value * 1e3, nb.value))
+        L.nlam_profile_enable(0)
+        return False
+
+    def names(self):
+        return [r[0] for r in self.rows]
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is None:

@@ -130,7 +130,7 @@ def test_training_step_gradients_match_oracle():
     gen = torch.Generator().manual_seed(5)
     prev, pprev, forc = torch.randn(2, G, 5, generator=gen), torch.randn(2, G, 5, generator=gen), torch.randn(2, G, 6, generator=gen)
     w = torch.randn(2, G, 5, generator=gen)
-    params = {k: v.clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
     out = rp.graph_model_forward(params, g, cfg, prev, pprev, forc)
     (out * w).sum().backward()
     m = m.cuda()

@@ -53,6 +53,12 @@ CASES = [
     ("empty_receivers", 40, 600, 300, 2, True, "sum", False, True, False),
     ("single_tile", 5, 4, 10, 1, True, "sum", False, True, False),
     ("deg128", 300, 3, 300, 2, False, "sum", False, True, False),
+    # batch-broadcast edge features, no edge update, large sender set -> tc_edge_bcast_kernel (tc6.cu)
+    ("bcast_g2m", 3000, 200, 2500, 3, False, "sum", False, True, True),
+    ("bcast_mean_b1", 3000, 200, 2500, 1, False, "mean", False, True, True),
+    ("bcast_many_items", 60000, 3000, 40000, 5, False, "sum", False, True, True),
+    ("bcast_deg100", 2000, 3, 300, 4, False, "sum", False, True, True),
+    ("bcast_empty_receivers", 5000, 900, 400, 2, False, "sum", False, True, True),
 ]
 
 
@@ -83,8 +89,11 @@ def test_edge_and_node_kernels_vs_oracle(case):
 
     ref_err, want = _ref_tf32_err(f64, fgpu)
     net = net.to(DEV)
-    with torch.no_grad():
+    with torch.no_grad(), ops.profile_launches() as prof:
         got = net(send.to(DEV), (send if same else rec).to(DEV), edge.to(DEV).expand(B, -1, -1))
+    if name.startswith("bcast"):
+        assert "tc_edge_bcast_kernel" in prof.names(), prof.names()
+    assert not any("simt" in n for n in prof.names()), prof.names()
     got = got if isinstance(got, tuple) else (got,)
     err = max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want))
     assert err <= ABS_TOL, (name, err)
