@@ -16,6 +16,9 @@ from . import _lib, ops
 from .networks import _aten_forward, make_mlp
 
 _DEFAULT_MATH = "auto"
+# in-place edge update of the middle layers of a stack: needs an edge kernel whose stores never touch rows of a
+# neighbouring tile (the reduce-add store of the v4 edge kernel); off while the library has none
+_INPLACE_EDGE_UPDATE = False
 _MATH_FLAGS = {"auto": 0, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}
 
 
@@ -302,6 +305,23 @@ class InteractionNet(nn.Module):
         if self.update_edges:
             return outs[0], outs[1]
         return outs[0]
+
+    @torch.no_grad()
+    def forward_stacked(self, node_rep, edge_rep, first, last):
+        """Inference-only entry for a layer inside a stack over ONE node set whose intermediate edge tensors are
+        private to the stack (``GNNSequential`` with ``keep_edge_rep=False``): the last layer does not write its
+        edge output (nobody reads it), a middle layer may update ``edge_rep`` in place (``first``: the incoming
+        tensor belongs to the caller — e.g. the cached static embedding — and is never written).  Same values as
+        ``forward``.  Returns ``(node_rep', edge_rep' | None)``."""
+        if not (self.update_edges and self._fusable() and self._is_sorted):
+            return self.forward(node_rep, node_rep, edge_rep)
+        self._check_inputs(node_rep, node_rep, edge_rep)
+        _, (s3, r3, e3) = self._batchify(node_rep, node_rep, edge_rep)
+        g = self._graph(r3.device)
+        inplace = _INPLACE_EDGE_UPDATE and (not first) and (not last) and e3.is_contiguous()
+        rec_out, edge_out, _ = ops.inet_fwd(g, self.edge_mlp, self.aggr_mlp, s3, r3, e3, not last, self._flags(),
+                                            edge_inplace=inplace)
+        return rec_out, edge_out
 
     def propagate(self, edge_index, x=None, edge_attr=None, size=None):
         """PyG-style entry kept for API compatibility (reference tests call it directly,

@@ -291,7 +291,7 @@ class GraphLAM(BaseGraphModel):
         """reference graph/graph_lam.py:157-188"""
         static = static or self.static_embeddings()
         B = mesh_rep.shape[0]
-        mesh_rep, _ = self.processor(mesh_rep, self.expand_to_batch(static["m2m_emb"], B))
+        mesh_rep, _ = self.processor(mesh_rep, self.expand_to_batch(static["m2m_emb"], B), keep_edge_rep=False)
         return mesh_rep
 
 

@@ -102,9 +102,17 @@ class GNNSequential(nn.Module):
     def __getitem__(self, i):
         return getattr(self, f"module_{i}")
 
-    def forward(self, mesh_rep, edge_rep):
+    def forward(self, mesh_rep, edge_rep, keep_edge_rep=True):
+        """``keep_edge_rep=False``: the caller discards the final edge representation (GraphLAM.process_step,
+        reference graph_lam.py:185 ``mesh_rep, _ = self.processor(...)``): in no-grad mode the last layer then
+        skips writing it, and the layers in between update their (private) edge tensor IN PLACE."""
+        fast = (not keep_edge_rep) and not torch.is_grad_enabled()
         for i in range(self._n):
-            mesh_rep, edge_rep = getattr(self, f"module_{i}")(mesh_rep, mesh_rep, edge_rep)
+            mod = getattr(self, f"module_{i}")
+            if fast and hasattr(mod, "forward_stacked"):
+                mesh_rep, edge_rep = mod.forward_stacked(mesh_rep, edge_rep, first=(i == 0), last=(i == self._n - 1))
+            else:
+                mesh_rep, edge_rep = mod(mesh_rep, mesh_rep, edge_rep)
         return mesh_rep, edge_rep
 
 

@@ -291,9 +291,10 @@ class SegmentSumFn(torch.autograd.Function):
         return gm, None, None, None, None
 
 
-def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags, want_aggr=False):
+def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags, want_aggr=False, edge_inplace=False):
     """One fused InteractionNet/PropagationNet forward through ``nlam_inet_fwd``.
-    ``edge_csr`` must be in CSR edge order.  Returns (rec_out, edge_out|None, aggr|None), 3-D."""
+    ``edge_csr`` must be in CSR edge order.  ``edge_inplace``: write e' = e + m over ``edge_csr`` itself (a dense
+    batched tensor the caller owns).  Returns (rec_out, edge_out|None, aggr|None), 3-D."""
     L = _lib.lib()
     s, Bs, sbs = as_rows(send)
     r, Br, rbs = as_rows(rec)
@@ -316,7 +317,10 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     em = mlp_struct(edge_seq)
     am = mlp_struct(aggr_seq)
     rec_out = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32)
-    edge_out = torch.empty((B, graph.n_edges, H), device=dev, dtype=torch.float32) if update_edges else None
+    if update_edges and edge_inplace and Be == B and (B == 1 or ebs == graph.n_edges * H):
+        edge_out = e
+    else:
+        edge_out = torch.empty((B, graph.n_edges, H), device=dev, dtype=torch.float32) if update_edges else None
     aggr = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32) if want_aggr else None
     ws_bytes = L.nlam_inet_workspace_bytes(graph.handle, B, H, flags)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)

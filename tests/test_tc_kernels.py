@@ -74,6 +74,8 @@ def test_edge_and_node_kernels_vs_oracle(case):
                 p.add_(0.1 * torch.randn_like(p))
     send = torch.randn(B, ns, 64)
     rec = send if same else torch.randn(B, nr, 64)
+    if name.startswith("bcast"):  # grid -> mesh shape: receivers and edge features are batch-broadcast static embeddings
+        rec = torch.randn(1, nr, 64).expand(B, -1, -1)
     edge = torch.randn(1 if expand else B, ne, 64)
     sd = dict(net.state_dict())
     sd64 = {k: v.double() for k, v in sd.items()}
@@ -89,8 +91,11 @@ def test_edge_and_node_kernels_vs_oracle(case):
 
     ref_err, want = _ref_tf32_err(f64, fgpu)
     net = net.to(DEV)
+    rec_dev = (send if same else rec).to(DEV)
+    if name.startswith("bcast"):
+        rec_dev = rec[:1].to(DEV).expand(B, -1, -1)  # stride-0 batch, as expand_to_batch hands it over
     with torch.no_grad(), ops.profile_launches() as prof:
-        got = net(send.to(DEV), (send if same else rec).to(DEV), edge.to(DEV).expand(B, -1, -1))
+        got = net(send.to(DEV), rec_dev, edge.to(DEV).expand(B, -1, -1))
     if name.startswith("bcast"):
         assert "tc_edge_bcast_kernel" in prof.names(), prof.names()
     assert not any("simt" in n for n in prof.names()), prof.names()
