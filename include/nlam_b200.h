@@ -56,6 +56,7 @@ extern "C" {
 #define NLAM_PROPAGATION 0x2      /* PropagationNet: msg = x_j + mlp(..), node residual = aggr */
 #define NLAM_MATH_TF32 0x10       /* tcgen05 TF32 tensor-core kernels (fp32 accumulate) */
 #define NLAM_MATH_FP32 0x20       /* exact fp32 FFMA kernels */
+#define NLAM_HINT_ONE_HIDDEN 0x100 /* promise to nlam_inet_workspace_bytes: both MLPs are Linear-SiLU-Linear-LayerNorm */
 /* neither math flag: TF32 when the shape is supported by the tensor-core kernels, else FP32 */
 
 #define NLAM_MAX_LINEAR 4

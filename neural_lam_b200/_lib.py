@@ -17,6 +17,7 @@ AGGR_MEAN = 0x1
 PROPAGATION = 0x2
 MATH_TF32 = 0x10
 MATH_FP32 = 0x20
+HINT_ONE_HIDDEN = 0x100
 E_UNSUPPORTED = 2  # NLAM_E_UNSUPPORTED
 
 c_float_p = ctypes.c_void_p  # device pointers travel as integers

@@ -2,6 +2,8 @@
 // kernels.  See include/nlam_b200.h for the contract and the reference interfaces replaced.
 #include "common.cuh"
 
+#include <algorithm>
+
 using namespace nlam;
 
 static bool want_tf32(int flags) { return !(flags & NLAM_MATH_FP32); }
@@ -13,6 +15,15 @@ extern "C" int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n
   cudaStream_t st = (cudaStream_t)stream;
   if (want_tf32(flags) && tc_rowmlp_supported(mlp, srcs, n_src, res, res2, n_rows))
     return tc_rowmlp(mlp, srcs, n_src, res, out, n_rows, B, st);
+  if (want_tf32(flags) && !out2 && tc_mlp2_supported(mlp, srcs, n_src, res, res2)) {
+    // H = 128 / 256: two launches of the generic tcgen05 Linear kernel; the hidden activations live in a
+    // stream-ordered scratch allocation (legal inside a stream capture)
+    float* ws = nullptr;
+    NLAM_CUDA_OK(cudaMallocAsync((void**)&ws, (size_t)n_rows * B * mlp->out_dim[0] * sizeof(float), st));
+    const int rc = tc_mlp2(mlp, srcs, n_src, res, out, n_rows, B, st, ws);
+    NLAM_CUDA_OK(cudaFreeAsync(ws, st));
+    return rc;
+  }
   NLAM_REQUIRE(!(flags & NLAM_MATH_TF32), NLAM_E_UNSUPPORTED,
                "nlam_rowmlp_fwd: shape not supported by the tcgen05 kernels (in=%d)", mlp->in_dim);
   return rowmlp_simt(mlp, srcs, n_src, res, res2, out, out2, n_rows, B, st);
@@ -32,14 +43,30 @@ extern "C" int nlam_rowmlp_step_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, 
   return tc_rowmlp(mlp, srcs, n_src, nullptr, new_state, n_rows, B, (cudaStream_t)stream, &ep);
 }
 
+static size_t rup256(size_t n) { return (n + 255) / 256 * 256; }
+
+// Workspace layout: [aggregate | path-specific scratch].  Sized per path: the fused H = 64 kernels need only the node
+// projections, the generic tensor-core path its projections / hidden activations / messages, the exact fp32 path the
+// message buffer.
+enum InetPath { PATH_EXACT = 0, PATH_TC64 = 1, PATH_GEN = 2 };
+static size_t inet_scratch_bytes(const NlamGraph* g, int B, int H, InetPath path) {
+  if (path == PATH_TC64) return rup256(tc_edge2_workspace_floats(g, B, 0) * sizeof(float));  // node projections
+  if (path == PATH_GEN) return rup256(tc_inet_gen_workspace_floats(g, B, H) * sizeof(float));
+  return rup256((size_t)B * g->n_edges * H * sizeof(float));  // exact path: messages
+}
+
 extern "C" size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, int flags) {
-  (void)flags;
   if (!g) return 0;
-  // message buffer (exact path) + aggregate buffer; 256-byte aligned sections
-  size_t msg = ((size_t)B * g->n_edges * H * sizeof(float) + 255) / 256 * 256;
-  size_t agg = ((size_t)B * g->n_rec * H * sizeof(float) + 255) / 256 * 256;
-  size_t proj = (H == 64) ? (tc_edge2_workspace_floats(g, B, 0) * sizeof(float) + 255) / 256 * 256 : 0;
-  return msg + agg + proj;
+  // the path is chosen from the MLP shapes at call time; without the NLAM_HINT_ONE_HIDDEN promise (both MLPs are
+  // Linear-SiLU-Linear-LayerNorm, the reference's hidden_layers = 1) the bound covers every path
+  const bool tf32 = !(flags & NLAM_MATH_FP32), prop = flags & NLAM_PROPAGATION, one = flags & NLAM_HINT_ONE_HIDDEN;
+  size_t need;
+  if (tf32 && one && H == 64 && !prop && g->n_tiles > 0) need = inet_scratch_bytes(g, B, H, PATH_TC64);
+  else if (tf32 && one && (H == 128 || H == 256 || (H == 64 && prop))) need = inet_scratch_bytes(g, B, H, PATH_GEN);
+  else if (!tf32) need = inet_scratch_bytes(g, B, H, PATH_EXACT);
+  else need = std::max(inet_scratch_bytes(g, B, H, PATH_EXACT),
+                       std::max(inet_scratch_bytes(g, B, H, PATH_TC64), inet_scratch_bytes(g, B, H, PATH_GEN)));
+  return rup256((size_t)B * g->n_rec * H * sizeof(float)) + need;
 }
 
 extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
@@ -56,51 +83,45 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int mean = (flags & (NLAM_AGGR_MEAN | NLAM_PROPAGATION)) ? 1 : 0;  // PropagationNet forces mean
   const bool prop = flags & NLAM_PROPAGATION;
-  const size_t msg_bytes = ((size_t)B * g->n_edges * H * sizeof(float) + 255) / 256 * 256;
-  const size_t agg_bytes = ((size_t)B * g->n_rec * H * sizeof(float) + 255) / 256 * 256;
-
+  const size_t agg_bytes = rup256((size_t)B * g->n_rec * H * sizeof(float));
   const bool use_tc = want_tf32(flags) && tc_edge_supported(g, edge_mlp, flags);
-  NLAM_REQUIRE(use_tc || !(flags & NLAM_MATH_TF32), NLAM_E_UNSUPPORTED,
+  const bool use_gen = !use_tc && want_tf32(flags) &&
+                       tc_inet_gen_supported(g, edge_mlp, aggr_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs);
+  const size_t scratch_bytes = inet_scratch_bytes(g, B, H, use_tc ? PATH_TC64 : use_gen ? PATH_GEN : PATH_EXACT);
+  NLAM_REQUIRE(workspace && ws_bytes >= agg_bytes + scratch_bytes, NLAM_E_WORKSPACE,
+               "nlam_inet_fwd: workspace too small (%zu < %zu bytes; see nlam_inet_workspace_bytes)", ws_bytes,
+               agg_bytes + scratch_bytes);
+  float* aggr = aggr_out ? aggr_out : (float*)workspace;
+  float* scratch = (float*)((char*)workspace + agg_bytes);
+  const int64_t aggr_bs = (int64_t)g->n_rec * H;
+
+  NLAM_REQUIRE(use_tc || use_gen || !(flags & NLAM_MATH_TF32), NLAM_E_UNSUPPORTED,
                "nlam_inet_fwd: shape (H=%d, max in-degree %d, hidden_layers=%d) not supported by the tcgen05 kernels",
                H, g->max_in_degree, edge_mlp->n_linear - 1);
-
-  float* aggr = aggr_out;
-  if (!aggr) {
-    NLAM_REQUIRE(workspace && ws_bytes >= msg_bytes + agg_bytes, NLAM_E_WORKSPACE, "nlam_inet_fwd: workspace too small");
-    aggr = (float*)((char*)workspace + msg_bytes);
-  }
-  const int64_t aggr_bs = (int64_t)g->n_rec * H;
+  if (use_gen)
+    return tc_inet_gen(g, edge_mlp, aggr_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, rec_out, edge_out, aggr, B, flags,
+                       scratch, st);
 
   if (use_tc) {
     // rows of the sender tensor: known exactly when the batches are dense, else at least n_send
     const int64_t send_rows = (B > 1 && send_bs > 0) ? send_bs / H : g->n_send;
-    const size_t proj_bytes = tc_edge2_workspace_floats(g, B, 0) * sizeof(float);
     int rc;
-    if (tc_ell_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge_out != nullptr) && workspace &&
-        ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
+    if (tc_ell_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge_out != nullptr)) {
       // uniform in-degree: receiver-tiled ELL kernel, aggregation in registers (tc3.cu)
-      rc = tc_ell_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, aggr, B, flags, st,
-                       (float*)((char*)workspace + msg_bytes + agg_bytes));
-    } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows) && workspace &&
-        ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
-      // split first Linear: node projections + K=64 edge kernel (tc2.cu)
-      float* proj = (float*)((char*)workspace + msg_bytes + agg_bytes);
-      rc = tc_edge3_enabled()
-               ? tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, proj)
-               : tc_edge2(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows, proj);
-    } else if (tc_edge_bcast_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs, B, edge_out != nullptr) &&
-               workspace && ws_bytes >= msg_bytes + agg_bytes + proj_bytes) {
-      // batch-broadcast edge features, large sender set, no edge update (grid -> mesh): tile-major kernel with the
-      // edge term resident in TMEM and raw sender rows gathered (tc6.cu)
-      rc = tc_edge_bcast(g, edge_mlp, send, send_bs, rec, rec_bs, edge, aggr, B, flags, st,
-                         (float*)((char*)workspace + msg_bytes + agg_bytes));
+      rc = tc_ell_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, aggr, B, flags, st, scratch);
+    } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows)) {
+      // split first Linear: node projections + K=64 edge kernel with sender windows (tc5.cu)
+      rc = tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
+    } else if (tc_edge_bcast_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs, B, edge_out != nullptr)) {
+      // batch-broadcast edge features and receivers, large sender set, no edge update (grid -> mesh): tile-major
+      // kernel with the edge term resident in TMEM and raw sender rows gathered (tc6.cu)
+      rc = tc_edge_bcast(g, edge_mlp, send, send_bs, rec, rec_bs, edge, aggr, B, flags, st, scratch);
     } else {
       rc = tc_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, send_rows);
     }
     if (rc) return rc;
   } else {
-    NLAM_REQUIRE(workspace && ws_bytes >= msg_bytes, NLAM_E_WORKSPACE, "nlam_inet_fwd: workspace too small");
-    float* msg = (float*)workspace;
+    float* msg = scratch;
     NlamRowSrc srcs[3] = {{edge, nullptr, edge_bs, H, 0}, {send, g->src, send_bs, H, 0}, {rec, g->dst, rec_bs, H, 0}};
     NlamRowSrc res = {send, g->src, send_bs, H, 0};
     NlamRowSrc res2 = {edge, nullptr, edge_bs, H, 0};

@@ -75,6 +75,45 @@ struct RowLinProblem {
   float* out;
 };
 int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st);
+// tc7.cu: generic tcgen05 Linear (any K multiple of 32, N <= 256) and the layer paths built from it
+struct LinearCall {
+  const float* x0;      // (B|1, n_rows, k0) dense rows
+  int64_t x0_bs;
+  int k0;
+  const float* x1;      // optional second K block (B|1, n_rows, k1)
+  int64_t x1_bs;
+  int k1;
+  const float* w;       // (n_out, k0 + k1) slice of a row-major matrix with row pitch ldw
+  int ldw;
+  const float* bias;    // optional (n_out)
+  int n_out;
+  int act;              // 0 none, 1 SiLU
+  const float* gamma;   // optional LayerNorm over the n_out columns
+  const float* beta;
+  float eps;
+  const float* add[2];  // optional gathered pre-activation addends: add[i][b, idx[i][r], :]
+  const int32_t* add_idx[2];
+  int64_t add_bs[2];
+  const float* post;    // optional gathered post-epilogue addend
+  const int32_t* post_idx;
+  int64_t post_bs;
+  const float* res;     // optional residual (row r)
+  int64_t res_bs;
+  int64_t n_rows;
+  int B;
+  float* out;           // (B, n_rows, n_out)
+  float* out2;          // optional: the value before the residual
+};
+int tc_linear(const LinearCall& c, cudaStream_t st);
+bool tc_mlp2_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2);
+int tc_mlp2(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows, int B,
+            cudaStream_t st, float* ws);
+bool tc_inet_gen_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, int flags, const float* send,
+                           int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs);
+size_t tc_inet_gen_workspace_floats(const NlamGraph* g, int B, int H);
+int tc_inet_gen(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const float* send, int64_t send_bs,
+                const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, float* rec_out, float* edge_out,
+                float* aggr, int B, int flags, float* ws, cudaStream_t st);
 // tc6.cu: batch-broadcast edge features, no edge update, raw sender rows gathered (grid -> mesh)
 bool tc_edge_bcast_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                              const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, int B, bool has_edge_out);

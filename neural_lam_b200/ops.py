@@ -322,7 +322,8 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     else:
         edge_out = torch.empty((B, graph.n_edges, H), device=dev, dtype=torch.float32) if update_edges else None
     aggr = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32) if want_aggr else None
-    ws_bytes = L.nlam_inet_workspace_bytes(graph.handle, B, H, flags)
+    hint = _lib.HINT_ONE_HIDDEN if (em.n_linear == 2 and am.n_linear == 2 and em.ln_gamma and am.ln_gamma) else 0
+    ws_bytes = L.nlam_inet_workspace_bytes(graph.handle, B, H, flags | hint)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
         _lib.check(L.nlam_inet_fwd(

@@ -105,6 +105,90 @@ def test_edge_and_node_kernels_vs_oracle(case):
     assert err <= max(3 * ref_err, 4e-3), (name, err, ref_err)
 
 
+GEN_CASES = [
+    # name, class, H, ns, nr, ne, B, update_edges, aggr, expanded edge
+    ("h128_sum_upd", "InteractionNet", 128, 300, 200, 1500, 2, True, "sum", False),
+    ("h128_mean_noupd_bcast", "InteractionNet", 128, 300, 200, 1500, 3, False, "mean", True),
+    ("h256_sum_upd", "InteractionNet", 256, 200, 150, 900, 2, True, "sum", False),
+    ("h256_b1_many_tiles", "InteractionNet", 256, 5000, 3000, 20000, 1, True, "sum", False),
+    ("h128_prop", "PropagationNet", 128, 120, 80, 700, 2, True, "sum", False),
+    ("h64_prop", "PropagationNet", 64, 120, 80, 700, 2, True, "sum", False),
+    ("h64_prop_noupd", "PropagationNet", 64, 120, 80, 700, 2, False, "sum", True),
+]
+
+
+@pytest.mark.parametrize("case", GEN_CASES, ids=[c[0] for c in GEN_CASES])
+def test_generic_tensor_core_path_vs_oracle(case):
+    """H = 128 / 256 (BASELINE configs 3-5) and PropagationNet: the generic tcgen05 Linear kernel (tc7.cu) — node
+    projections, two edge layers, CSR segment sum, two node layers — against the fp64 oracle, same bound as above."""
+    name, cls, H, ns, nr, ne, B, upd, aggr, expand = case
+    ei = _graph(ns, nr, ne, 3, True)
+    torch.manual_seed(0)
+    net = getattr(nlb, cls)(ei, H, update_edges=upd, aggr=aggr, math="tf32")
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    send, rec = torch.randn(B, ns, H), torch.randn(B, nr, H)
+    edge = torch.randn(1 if expand else B, ne, H)
+    prop = cls == "PropagationNet"
+    sd = dict(net.state_dict())
+    sd64 = {k: v.double() for k, v in sd.items()}
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+
+    def f64():
+        return rp.interaction_net(sd64, ei, send.double(), rec.double(), edge.double().expand(B, -1, -1), aggr=aggr,
+                                  update_edges=upd, propagation=prop)
+
+    def fgpu():
+        return rp.interaction_net(sdg, ei.to(DEV), send.to(DEV), rec.to(DEV), edge.to(DEV).expand(B, -1, -1), aggr=aggr,
+                                  update_edges=upd, propagation=prop)
+
+    ref_err, want = _ref_tf32_err(f64, fgpu)
+    net = net.to(DEV)
+    with torch.no_grad(), ops.profile_launches() as prof:
+        got = net(send.to(DEV), rec.to(DEV), edge.to(DEV).expand(B, -1, -1))
+    names = prof.names()
+    assert any(n.startswith("tc_linear_kernel") for n in names) and not any("rowmlp_simt" in n for n in names), names
+    got = got if isinstance(got, tuple) else (got,)
+    err = max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want))
+    print(f"{name}: err {err:.3e} (reference TF32 config {ref_err:.3e}); launches {names}")
+    assert err <= ABS_TOL, (name, err)
+    assert err <= max(3 * ref_err, 4e-3), (name, err, ref_err)
+
+
+GEN_ROW_CASES = [
+    ("h128_embed", [128, 128, 128], [(2, 700, 128)], None, True),
+    ("h128_node_res", [256, 128, 128], [(2, 333, 128), (2, 333, 128)], 0, True),
+    ("h256_node_res_aggr", [512, 256, 256], [(1, 1000, 256), (1, 1000, 256)], 1, True),
+    ("h256_bcast_in", [256, 256, 256], [(500, 256)], None, True),
+    ("h128_output_map_17", [128, 128, 17], [(2, 400, 128)], None, False),
+]
+
+
+@pytest.mark.parametrize("case", GEN_ROW_CASES, ids=[c[0] for c in GEN_ROW_CASES])
+def test_generic_row_mlp_vs_oracle(case):
+    name, blueprint, shapes, res_i, ln = case
+    torch.manual_seed(1)
+    mlp = nlb.make_mlp(blueprint, layer_norm=ln)
+    srcs = [torch.randn(*sh) for sh in shapes]
+    sd64 = {f"m.{k}": v.double() for k, v in mlp.state_dict().items()}
+    B = max((t.shape[0] for t in srcs if t.dim() == 3), default=1)
+    cat64 = torch.cat([(t if t.dim() == 3 else t.unsqueeze(0).expand(B, -1, -1)).double() for t in srcs], dim=-1)
+    want = rp.mlp(cat64, sd64, "m", 1, layer_norm=ln)
+    if res_i is not None:
+        want = want + srcs[res_i].double()
+    mlp = mlp.to(DEV)
+    mlp.nlam_flags = _lib.MATH_TF32
+    with torch.no_grad(), ops.profile_launches() as prof:
+        got = mlp.apply_rows([t.to(DEV) for t in srcs], res=None if res_i is None else srcs[res_i].to(DEV))
+    assert all(n.startswith("tc_linear_kernel") for n in prof.names()), prof.names()
+    got = got if got.dim() == 3 else got.unsqueeze(0)
+    err = (got.double().cpu() - want).abs().max().item()
+    print(f"{name}: err {err:.3e}")
+    assert err <= ABS_TOL, (name, err)
+
+
 def test_tf32_requested_but_unsupported_raises_and_auto_falls_back():
     ei = _graph(50, 3, 500, 0, True)  # in-degree > 128: outside the tensor-core tile table
     for H, ok_auto in ((64, True), (16, True)):
