@@ -41,10 +41,21 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-GRID = (238, 268)
-HIDDEN = 64
-PROC_LAYERS = 4
 D_STATE, D_FORCING, D_STATIC = 17, 18, 4
+# BASELINE.json configs (1-based as listed there).  Config 2 is the one the metric is quoted on (default); 3 and 4 are
+# the H = 128 / 256 workloads (generic tcgen05 path, tc7.cu), 4 as its single-GPU form (B = 1).
+CONFIGS = {
+    2: dict(grid=(238, 268), hierarchical=False, n_levels=None, model="graph_lam", hidden=64, layers=4, batch=32,
+            workload="MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers (BASELINE.json configs[1])"),
+    3: dict(grid=(238, 268), hierarchical=True, n_levels=3, model="hi_lam", hidden=128, layers=6, batch=8,
+            workload="MEPS 268x238 grid, 3-level hierarchical mesh, HiLAM hidden_dim=128, 6 processor layers "
+                     "(BASELINE.json configs[2])"),
+    4: dict(grid=(1024, 1024), hierarchical=False, n_levels=None, model="graph_lam", hidden=256, layers=4, batch=1,
+            workload="synthetic 1024x1024 grid, multiscale mesh, GraphLAM hidden_dim=256, 4 processor layers, whole graph on "
+                     "ONE GPU (single-GPU form of BASELINE.json configs[3])"),
+}
+CFG = CONFIGS[2]
+METRIC = "forecast-steps/sec (268x238 grid, hidden=64)"
 
 
 def _peaks():
@@ -54,6 +65,14 @@ def _peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _bf16_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f).get("bf16_tflops_sustained", 1406.5))
+    return 1400.0
 
 
 class ClockSampler:
@@ -106,10 +125,10 @@ class ClockSampler:
 def build_model(device, math="auto"):
     from neural_lam_b200 import models, synthetic
 
-    spec = synthetic.make_graph_spec(*GRID, hierarchical=False)
+    spec = synthetic.make_graph_spec(*CFG["grid"], hierarchical=CFG["hierarchical"], n_levels=CFG["n_levels"])
     ds = synthetic.SyntheticDatastore(spec, d_state=D_STATE, d_forcing=D_FORCING, d_static=D_STATIC, boundary_width=10)
     torch.manual_seed(42)
-    model = models.GraphLAM(ds, spec, hidden_dim=HIDDEN, processor_layers=PROC_LAYERS, math=math)
+    model = models.MODELS[CFG["model"]](ds, spec, hidden_dim=CFG["hidden"], processor_layers=CFG["layers"], math=math)
     fc = models.ARForecaster(model, ds)
     if device is not None:
         fc = fc.to(device)
@@ -130,13 +149,18 @@ def synth_inputs(B, T, G, seed=123, pin=False):
 def oracle_setup(model, fc):
     from oracle import reference_port as rp  # noqa: F401  (CPU baseline leg only)
 
+    from neural_lam_b200 import models
+
     g = {}
     for k in ("grid_static_features", "g2m_features", "m2g_features", "g2m_edge_index", "m2g_edge_index",
-              "diff_std", "diff_mean", "m2m_features", "m2m_edge_index", "mesh_static_features"):
-        g[k] = getattr(model, k).detach().cpu()
+              "diff_std", "diff_mean", "m2m_features", "m2m_edge_index", "mesh_static_features", "mesh_up_features",
+              "mesh_up_edge_index", "mesh_down_features", "mesh_down_edge_index"):
+        if hasattr(model, k):
+            v = getattr(model, k)
+            g[k] = [t.detach().cpu() for t in v] if isinstance(v, models.BufferList) else v.detach().cpu()
     g["boundary_mask"] = fc.boundary_mask.detach().cpu()
     params = {f"predictor.{k}": v.detach().cpu() for k, v in model.state_dict().items()}
-    cfg = dict(model="graph_lam", hidden_layers=1, processor_layers=PROC_LAYERS, mesh_aggr="sum")
+    cfg = dict(model=CFG["model"], hidden_layers=1, processor_layers=CFG["layers"], mesh_aggr="sum")
     return params, g, cfg
 
 
@@ -181,8 +205,9 @@ def algorithmic_bytes_inet(B, Ns, Nr, E, H, update_edges, same_nodes):
 def roofline_m2m(model, B, device, iters=20):
     """Time one m2m processor layer (all launches of nlam_inet_fwd) with L2 flushed between
     iterations; achieved = algorithmic bytes / mean CUDA-event time."""
-    layer = model.processor[0]
-    Nm, E, H = model.num_mesh_nodes, layer.num_edges, HIDDEN
+    # GraphLAM: a processor layer over the multiscale mesh; HiLAM: the level-0 same-level layer of the first sweep
+    layer = model.processor[0] if hasattr(model, "processor") else model.mesh_down_same_gnns[0][0]
+    Nm, E, H = layer.num_rec, layer.num_edges, CFG["hidden"]
     g = torch.Generator(device="cpu").manual_seed(7)
     mesh = torch.randn(B, Nm, H, generator=g).to(device)
     edge = torch.randn(B, E, H, generator=g).to(device)
@@ -242,7 +267,7 @@ def time_ref_cuda(model, fc, device, B, steps, warmup):
 
     params, g, cfg = oracle_setup(model, fc)
     params = {k: v.to(device) for k, v in params.items()}
-    g = {k: v.to(device) for k, v in g.items()}
+    g = {k: ([t.to(device) for t in v] if isinstance(v, list) else v.to(device)) for k, v in g.items()}
     G = model.num_grid_nodes
     init, forc, bnd = (t.to(device) for t in synth_inputs(B, steps + warmup, G, seed=321))
     old = torch.get_float32_matmul_precision()
@@ -279,6 +304,28 @@ def parity_check(model, fc, device, B=2):
     return {"max_abs": err.max().item(), "max_rel": (err / want.abs().clamp(min=1.0)).max().item(),
             "reference_tf32_max_abs": (ref.double() - want).abs().max().item(),
             "what": f"1 forecast step, B={B}, real-size workload, vs fp64 oracle (rel = |err|/max(|x|,1))"}
+
+
+def step_algorithmic(model, B):
+    """Algorithmic fp32 bytes and FLOPs of one forecast step of B forecasts (SURVEY.md 8d formulas: every InteractionNet
+    call + the grid-side MLPs; input-independent embedders excluded, they are cached)."""
+    from neural_lam_b200.gnn_layers import InteractionNet
+
+    H = CFG["hidden"]
+    G = model.num_grid_nodes
+    nbytes = flops = 0.0
+    for name, mod in model.named_modules():
+        if isinstance(mod, InteractionNet):
+            E, Nr = mod.num_edges, mod.num_rec
+            Ns = mod.num_send_min
+            same = name.startswith(("processor", "mesh_down_same", "mesh_up_same"))
+            nbytes += algorithmic_bytes_inet(B, Ns, Nr, E, H, mod.update_edges, same)
+            flops += B * (8.0 * H * H * E + 6.0 * H * H * Nr)
+    d_in = D_STATE * 2 + D_FORCING + D_STATIC
+    rows = float(B) * G
+    nbytes += 4 * rows * (d_in + H) + 4 * rows * 2 * H + 4 * rows * (H + 3 * D_STATE)   # embedder, encoding, output_map+epilogue
+    flops += 2 * rows * (d_in * H + H * H) + 2 * rows * 2 * H * H + 2 * rows * (H * H + H * D_STATE)
+    return nbytes, flops
 
 
 def run_ours(args):
@@ -378,6 +425,13 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get("m2m_layer_dram_bytes", {}).get(str(B))
             except Exception:
                 traffic = None
+        sb, sf = step_algorithmic(model, B)
+        t_step = dev_ms / K * 1e-3
+        tf32_peak = 0.5 * _bf16_peak()
+        step_roof = {"algorithmic_bytes": sb, "flops": sf, "hbm_gbs": sb / t_step / 1e9, "hbm_frac": sb / t_step / 1e9 / peak,
+                     "tflops": sf / t_step / 1e12, "tensor_frac": sf / t_step / 1e12 / tf32_peak,
+                     "tensor_peak": tf32_peak, "tensor_peak_source": "0.5 x measured dense bf16 (MEASURED_PEAKS.json); a TF32 "
+                     "peak was not measured", "binding": "tensor" if sf / tf32_peak / 1e12 > sb / peak / 1e9 else "hbm"}
         kernels = kernel_table(fc, bufs, peak)
         parity = None if args.no_parity else parity_check(model, fc, device)
         ref_cuda = None
@@ -397,7 +451,7 @@ def run_ours(args):
         h2d = B * G * (D_FORCING + D_STATE) * 4
         d2h = B * G * D_STATE * 4
         line = {
-            "metric": "forecast-steps/sec (268x238 grid, hidden=64)",
+            "metric": METRIC,
             "value": world * B * K / (dev_ms * 1e-3),
             "unit": "forecast-steps/s",
             "n_gpus": world, "steps": K, "warmup": W,
@@ -405,8 +459,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 I/O; " + ("tf32 tensor-core MLPs, f32 accumulate" if args.math != "fp32" else "f32 FFMA"),
             "data": "synthetic",
-            "config": {"workload": "MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": CFG["workload"],
                        "batch_per_gpu": B, "global_batch": world * B, "math": args.math,
                        "parallelism": f"replicas x{world} (independent forecasts per GPU, no collective)",
                        "l2": "per-step working set (~0.36 GB x B algorithmic) exceeds the 126 MB L2; "
@@ -421,6 +474,7 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": nbytes, "ms_mean": mean_ms, "ms_median": med_ms,
                          "peak_source": peak_src, "l2_flushed": True},
+            "step_roofline": step_roof,
             "cpu_baseline": cpu,
             "ref_cuda": ref_cuda,
             "parity": parity,
@@ -451,12 +505,11 @@ def run_reference(args):
     v, sec, cores = time_cpu_reference(params, g, cfg, model.num_grid_nodes, steps=k, warmup=min(W, 1), B=B)
     line = {
         "impl": "reference",
-        "metric": "forecast-steps/sec (268x238 grid, hidden=64)",
+        "metric": METRIC,
         "value": v, "unit": "forecast-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": K, "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers "
-                               "(BASELINE.json configs[1])", "batch_per_gpu": B, "global_batch": B,
+        "config": {"workload": CFG["workload"], "batch_per_gpu": B, "global_batch": B,
                    "math": "f32 (torch CPU)", "parallelism": "host cores of one box"},
         "cpu_baseline": {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
                          "sample": f"each step = one forecast step of B={B} forecasts on the host cores; {k} timed steps "
@@ -472,13 +525,26 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="independent forecasts (ensemble members) per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (1-based): 2 = the metric's workload (default), 3 = HiLAM H=128, 4 = 1024^2 H=256")
+    ap.add_argument("--batch", type=int, default=0, help="independent forecasts (ensemble members) per GPU per step "
+                                                          "(default: 32 / 8 / 1 for configs 2 / 3 / 4)")
     ap.add_argument("--math", default="auto", choices=["auto", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--cpu-at-scale", action="store_true", help="time the CPU port even for config 4 (minutes)")
     args = ap.parse_args()
+    global CFG, METRIC
+    CFG = CONFIGS[args.config]
+    METRIC = ("forecast-steps/sec (268x238 grid, hidden=64)" if args.config == 2 else
+              f"forecast-steps/sec ({CFG['grid'][1]}x{CFG['grid'][0]} grid, hidden={CFG['hidden']}, BASELINE config {args.config})")
+    if not args.batch:
+        args.batch = CFG["batch"]
+    if args.config == 4:  # the fp64 / fp32 CPU oracle takes minutes per step at 1 M grid nodes
+        args.no_parity = True
+        args.no_cpu_baseline = args.no_cpu_baseline or not args.cpu_at_scale
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -24,6 +24,14 @@ extern "C" int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n
     NLAM_CUDA_OK(cudaFreeAsync(ws, st));
     return rc;
   }
+  if (want_tf32(flags) && !out2 && tc_mlp2_packed_supported(mlp, srcs, n_src, res, res2)) {
+    // narrow / concatenated inputs at H = 128 / 256: pack, then the two generic Linear launches
+    float* ws = nullptr;
+    NLAM_CUDA_OK(cudaMallocAsync((void**)&ws, tc_mlp2_packed_workspace_floats(mlp, n_rows, B) * sizeof(float), st));
+    const int rc = tc_mlp2_packed(mlp, srcs, n_src, out, n_rows, B, st, ws);
+    NLAM_CUDA_OK(cudaFreeAsync(ws, st));
+    return rc;
+  }
   NLAM_REQUIRE(!(flags & NLAM_MATH_TF32), NLAM_E_UNSUPPORTED,
                "nlam_rowmlp_fwd: shape not supported by the tcgen05 kernels (in=%d)", mlp->in_dim);
   return rowmlp_simt(mlp, srcs, n_src, res, res2, out, out2, n_rows, B, st);

@@ -85,6 +85,7 @@ struct LinearCall {
   int k1;
   const float* w;       // (n_out, k0 + k1) slice of a row-major matrix with row pitch ldw
   int ldw;
+  int w_cols;           // real columns of W (0: k0 + k1); columns past it read as zero (zero-padded inputs)
   const float* bias;    // optional (n_out)
   int n_out;
   int act;              // 0 none, 1 SiLU
@@ -108,6 +109,10 @@ int tc_linear(const LinearCall& c, cudaStream_t st);
 bool tc_mlp2_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2);
 int tc_mlp2(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows, int B,
             cudaStream_t st, float* ws);
+bool tc_mlp2_packed_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2);
+size_t tc_mlp2_packed_workspace_floats(const NlamMlp* m, int64_t n_rows, int B);
+int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* out, int64_t n_rows, int B, cudaStream_t st,
+                   float* ws);
 bool tc_inet_gen_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, int flags, const float* send,
                            int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs);
 size_t tc_inet_gen_workspace_floats(const NlamGraph* g, int B, int H);

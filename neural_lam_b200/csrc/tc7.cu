@@ -308,7 +308,7 @@ int tc_linear(const LinearCall& c, cudaStream_t st) {
     ma1 = ma0;
   }
   // W: (n_out rows, k0 + k1 columns) slice of a row-major matrix with row pitch ldw; rows past n_out read as zero
-  rc = make_map(&mw, c.w, (uint64_t)(c.k0 + c.k1), (uint64_t)c.n_out, 1, (uint64_t)c.ldw, (uint64_t)c.n_out * c.ldw, (uint32_t)N,
+  rc = make_map(&mw, c.w, (uint64_t)(c.w_cols ? c.w_cols : c.k0 + c.k1), (uint64_t)c.n_out, 1, (uint64_t)c.ldw, (uint64_t)c.n_out * c.ldw, (uint32_t)N,
                 true);
   if (rc) return rc;
   LinParams p;
@@ -437,6 +437,76 @@ int tc_mlp2(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSr
   d.B = B;
   d.out = out;
   return tc_linear(d, st);
+}
+
+// ---- narrow / concatenated inputs (grid embedder: prev | prev_prev | forcing | static, reference graph/base.py:275-283)
+// at H = 128 / 256: the sources are packed into one zero-padded dense (rows, Kp) block first, then the two Linear launches
+__global__ void pack_rows_kernel(const float* s0, const float* s1, const float* s2, const float* s3, int d0, int d1, int d2,
+                                 int d3, long long bs0, long long bs1, long long bs2, long long bs3, float* out, int kp,
+                                 long long n_rows, int B) {
+  const long long total = (long long)B * n_rows * kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kp);
+    const long long r = (i / kp) % n_rows;
+    const int b = (int)(i / ((long long)kp * n_rows));
+    float v = 0.f;
+    int cc = c;
+    if (cc < d0) v = s0[b * bs0 + r * d0 + cc];
+    else if ((cc -= d0) < d1) v = s1[b * bs1 + r * d1 + cc];
+    else if ((cc -= d1) < d2) v = s2[b * bs2 + r * d2 + cc];
+    else if ((cc -= d2) < d3) v = s3[b * bs3 + r * d3 + cc];
+    out[i] = v;
+  }
+}
+
+bool tc_mlp2_packed_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2) {
+  if (m->n_linear != 2 || res || res2 || n_src < 1 || n_src > 4) return false;
+  const int H = m->out_dim[0], no = m->out_dim[1];
+  if (!(H == 128 || H == 256) || no < 1 || no > 256 || (m->ln_gamma && no != npad(no))) return false;
+  int k = 0;
+  for (int s = 0; s < n_src; ++s) {
+    if (srcs[s].idx) return false;
+    k += srcs[s].dim;
+  }
+  return k == m->in_dim && k % 4 == 0 && k <= 1024 && aligned16(m->w[0]) && aligned16(m->w[1]);
+}
+
+size_t tc_mlp2_packed_workspace_floats(const NlamMlp* m, int64_t n_rows, int B) {
+  const int kp = (m->in_dim + 31) / 32 * 32;
+  return (size_t)n_rows * B * (kp + m->out_dim[0]);
+}
+
+int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* out, int64_t n_rows, int B, cudaStream_t st,
+                   float* ws) {
+  const int kp = (m->in_dim + 31) / 32 * 32, H = m->out_dim[0], no = m->out_dim[1];
+  float* packed = ws;
+  float* hid = ws + (size_t)n_rows * B * kp;
+  const float* sp[4] = {nullptr, nullptr, nullptr, nullptr};
+  int d[4] = {0, 0, 0, 0};
+  long long bs[4] = {0, 0, 0, 0};
+  for (int s = 0; s < n_src; ++s) {
+    sp[s] = srcs[s].ptr;
+    d[s] = srcs[s].dim;
+    bs[s] = B > 1 ? srcs[s].bstride : 0;
+  }
+  const long long total = (long long)B * n_rows * kp;
+  {
+    ProfScope ps("pack_rows_kernel", st, 4.0 * total + 4.0 * (double)B * n_rows * m->in_dim);
+    pack_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+        sp[0], sp[1], sp[2], sp[3], d[0], d[1], d[2], d[3], bs[0], bs[1], bs[2], bs[3], packed, kp, n_rows, B);
+  }
+  count_launch();
+  NLAM_CUDA_OK(cudaGetLastError());
+  LinearCall c;
+  memset(&c, 0, sizeof(c));
+  c.x0 = packed; c.x0_bs = (int64_t)n_rows * kp; c.k0 = kp; c.w = m->w[0]; c.ldw = m->in_dim; c.w_cols = m->in_dim;
+  c.bias = m->b[0]; c.n_out = H; c.act = 1; c.n_rows = n_rows; c.B = B; c.out = hid;
+  int rc = tc_linear(c, st);
+  if (rc) return rc;
+  memset(&c, 0, sizeof(c));
+  c.x0 = hid; c.x0_bs = (int64_t)n_rows * H; c.k0 = H; c.w = m->w[1]; c.ldw = H; c.bias = m->b[1]; c.n_out = no;
+  c.gamma = m->ln_gamma; c.beta = m->ln_beta; c.eps = m->ln_eps; c.n_rows = n_rows; c.B = B; c.out = out;
+  return tc_linear(c, st);
 }
 
 // ---- InteractionNet / PropagationNet (reference gnn_layers.py:110-157, :231-249) from the generic Linear kernel ----

@@ -140,3 +140,45 @@ def test_training_step_gradients_match_oracle():
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         torch.testing.assert_close(p.grad.cpu(), params[k].grad, rtol=2e-3, atol=2e-4, msg=lambda s: f"{k}: {s}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,hidden", [("hi_lam", 128), ("graph_lam_multiscale", 256)])
+def test_wide_hidden_models_run_on_the_generic_tensor_core_path(kind, hidden):
+    """BASELINE configs 3-5 use hidden_dim 128 / 256: every per-step launch is the generic tcgen05 Linear kernel (tc7.cu)
+    or an index kernel — no FFMA row-MLP — and the rollout matches the fp64 oracle within the TF32 bound
+    (|err| <= max(3 x the reference's TF32 configuration, 1e-2), as in tests/test_real_size.py)."""
+    from neural_lam_b200 import ops
+
+    # grid input width 5 + 5 + 6 + 4 = 20 (a multiple of 4, like the MEPS-shaped 56: rows the packed-input path takes)
+    spec = synthetic.make_graph_spec(30, 27, hierarchical=(kind == "hi_lam"))
+    ds = synthetic.SyntheticDatastore(spec, d_state=5, d_forcing=6, d_static=4, boundary_width=2)
+    torch.manual_seed(42)
+    m = (models.HiLAM if kind == "hi_lam" else models.GraphLAM)(ds, spec, hidden_dim=hidden, processor_layers=1, math="auto")
+    fc = models.ARForecaster(m, ds)
+    g = _oracle_graph(m, fc)
+    cfg = dict(model="hi_lam" if kind == "hi_lam" else "graph_lam", hidden_layers=1, processor_layers=1, mesh_aggr="sum")
+    G = m.num_grid_nodes
+    gen = torch.Generator().manual_seed(11)
+    B, T = 2, 2
+    init, forc, bnd = torch.randn(B, 2, G, 5, generator=gen), torch.randn(B, T, G, 6, generator=gen), torch.randn(B, T, G, 5, generator=gen)
+    params = {f"predictor.{k}": v for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        want64 = rp.ar_rollout({k: v.double() for k, v in params.items()}, g, cfg, init.double(), forc.double(), bnd.double())
+        with rp.tf32_matmul():
+            ref = rp.ar_rollout(params, g, cfg, init, forc, bnd)
+    fc = fc.to("cuda").eval()
+    with torch.no_grad():
+        got, _ = fc(init.cuda(), forc.cuda(), bnd.cuda())          # first call also fills the static-embedding cache
+        with ops.profile_launches() as prof:
+            got2, _ = fc(init.cuda(), forc.cuda(), bnd.cuda())
+        graphed = fc.rollout_graphed(init.cuda(), forc.cuda(), bnd.cuda())
+    names = set(prof.names())
+    assert not any("rowmlp_simt" in n for n in names), names
+    assert any(n.startswith("tc_linear_kernel") for n in names), names
+    torch.testing.assert_close(got2, got, rtol=0, atol=0)
+    torch.testing.assert_close(graphed, got, rtol=1e-6, atol=1e-6)
+    err = (got.cpu().double() - want64).abs().max().item()
+    ref_err = (ref.double() - want64).abs().max().item()
+    print(f"{kind} H={hidden}: max |err| vs fp64 oracle {err:.3e} (reference TF32 configuration {ref_err:.3e}); kernels {sorted(names)}")
+    assert err <= max(3 * ref_err, 1e-2), (err, ref_err)

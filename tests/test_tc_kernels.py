@@ -163,6 +163,8 @@ GEN_ROW_CASES = [
     ("h256_node_res_aggr", [512, 256, 256], [(1, 1000, 256), (1, 1000, 256)], 1, True),
     ("h256_bcast_in", [256, 256, 256], [(500, 256)], None, True),
     ("h128_output_map_17", [128, 128, 17], [(2, 400, 128)], None, False),
+    ("h128_grid_embedder_56", [56, 128, 128], [(2, 400, 17), (2, 400, 17), (2, 400, 18), (400, 4)], None, True),
+    ("h256_edge_embedder_3", [4, 256, 256], [(900, 4)], None, True),
 ]
 
 
@@ -182,7 +184,7 @@ def test_generic_row_mlp_vs_oracle(case):
     mlp.nlam_flags = _lib.MATH_TF32
     with torch.no_grad(), ops.profile_launches() as prof:
         got = mlp.apply_rows([t.to(DEV) for t in srcs], res=None if res_i is None else srcs[res_i].to(DEV))
-    assert all(n.startswith("tc_linear_kernel") for n in prof.names()), prof.names()
+    assert all(n.startswith(("tc_linear_kernel", "pack_rows")) for n in prof.names()), prof.names()
     got = got if got.dim() == 3 else got.unsqueeze(0)
     err = (got.double().cpu() - want).abs().max().item()
     print(f"{name}: err {err:.3e}")
