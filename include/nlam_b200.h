@@ -161,6 +161,16 @@ int nlam_gather_rows(const float* x, int64_t x_bstride, const int32_t* idx, int6
                      float* out, int64_t out_bstride, int B, int H, const int32_t* deg_ptr,
                      void* stream);
 
+/* Node-partitioned rollout (one process per GPU): copy this rank's own sender rows (B, n_own, H) into the front of its
+ * extended buffer ext_local (B, ext rows, H; batch stride ext_bs, the same on every rank) and store the rows listed in
+ * send_rows[send_ptr[p] .. send_ptr[p+1]) into peer p's extended buffer peer_ext[p] (a DEVICE array of `world`
+ * pointers to the peers' buffers mapped into this process: CUDA IPC / symmetric memory) at rows peer_dst_off[p] .. —
+ * direct stores over NVLink from this kernel.  The caller issues a cross-rank barrier before the buffers are read.
+ * Replaces the pack + NCCL send/recv + concatenation of a halo exchange. */
+int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, float* ext_local, int64_t ext_bs,
+                   float* const* peer_ext, const int32_t* send_rows, const int32_t* send_ptr,
+                   const int32_t* peer_dst_off, int64_t n_send_total, int world, int B, int H, void* stream);
+
 /* new_state = bmask * boundary + (1-bmask) * (prev + net_out*diff_std + diff_mean)
  * over (B,G,D); bmask (G), diff_std/mean (D); boundary may be NULL (then bmask ignored). */
 int nlam_step_epilogue(const float* net_out, const float* prev, const float* boundary,

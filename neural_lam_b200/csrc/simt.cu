@@ -434,3 +434,54 @@ extern "C" int nlam_step_epilogue(const float* net_out, const float* prev, const
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Halo push (node-partitioned rollout): ONE launch copies this rank's OWN sender rows into the front of
+// its extended buffer [own rows | halo rows] and stores the boundary rows its peers need DIRECTLY into their halo
+// regions — `peer_ext[p]` are the peers' extended buffers mapped into this process (CUDA IPC / symmetric memory), so
+// the stores travel over NVLink / NVSwitch from this kernel; no pack buffer, no NCCL send/recv, no concatenation.
+// The consumer side only needs a cross-rank barrier before it reads its extended buffer.
+__global__ void halo_push_kernel(const float* __restrict__ own, long long own_bs, long long n_own, float* ext_local,
+                                 long long ext_bs, float* const* __restrict__ peer_ext, const int32_t* __restrict__ send_rows,
+                                 const int32_t* __restrict__ send_ptr, const int32_t* __restrict__ peer_dst_off, int world,
+                                 int B, int H4) {
+  const long long n_send = send_ptr[world];
+  const long long per_b = (n_own + n_send) * H4;
+  const long long total = (long long)B * per_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long j = i - (long long)b * per_b;
+    const long long r = j / H4;
+    const int c = (int)(j - r * H4);
+    if (r < n_own) {
+      reinterpret_cast<float4*>(ext_local + b * ext_bs)[r * H4 + c] = reinterpret_cast<const float4*>(own + b * own_bs)[r * H4 + c];
+    } else {
+      const long long k = r - n_own;  // index into the concatenated send lists
+      int p = 0;
+      while (k >= send_ptr[p + 1]) ++p;  // world <= 8
+      const long long dst_row = peer_dst_off[p] + (k - send_ptr[p]);
+      reinterpret_cast<float4*>(peer_ext[p] + b * ext_bs)[dst_row * H4 + c] =
+          reinterpret_cast<const float4*>(own + b * own_bs)[(long long)send_rows[k] * H4 + c];
+    }
+  }
+}
+
+extern "C" int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, float* ext_local, int64_t ext_bs,
+                              float* const* peer_ext, const int32_t* send_rows, const int32_t* send_ptr,
+                              const int32_t* peer_dst_off, int64_t n_send_total, int world, int B, int H, void* stream) {
+  NLAM_REQUIRE(own && ext_local && peer_ext && send_ptr && peer_dst_off && world >= 1 && B >= 1 && H >= 4 && H % 4 == 0,
+               NLAM_E_INVALID, "halo_push: bad arguments");
+  NLAM_REQUIRE(own_bs % 4 == 0 && ext_bs % 4 == 0 && ((uintptr_t)own % 16 == 0) && ((uintptr_t)ext_local % 16 == 0),
+               NLAM_E_INVALID, "halo_push: rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * (n_own + n_send_total) * (H / 4);
+  if (total == 0) return NLAM_OK;
+  {
+    ProfScope ps("halo_push_kernel", st, 8.0 * total * 4);
+    halo_push_kernel<<<grid_for(total, 256), 256, 0, st>>>(own, own_bs, n_own, ext_local, ext_bs, peer_ext, send_rows, send_ptr,
+                                                           peer_dst_off, world, B, H / 4);
+  }
+  count_launch();
+  NLAM_CUDA_OK(cudaGetLastError());
+  return NLAM_OK;
+}

@@ -83,6 +83,9 @@ class InteractionNet(nn.Module):
     """
 
     propagation = False
+    # node-partitioned rollout (dist.partition_model): callable mapping this rank's OWN sender rows (B, n_own, H) to
+    # the extended rows [own | halo] the layer's local edge_index refers to
+    _halo = None
 
     def __init__(self, edge_index, input_dim, update_edges=True, hidden_layers=1, hidden_dim=None,
                  edge_chunk_sizes=None, aggr_chunk_sizes=None, aggr="sum", math=None):
@@ -288,6 +291,10 @@ class InteractionNet(nn.Module):
 
         send_rep ``(…, num_send, H)``, rec_rep ``(…, num_rec, H)``, edge_rep ``(…, E, H)`` ->
         rec_rep' or ``(rec_rep', edge_rep')`` when ``update_edges``."""
+        if self._halo is not None:  # node-partitioned rollout: own sender rows -> [own | halo]
+            send_rep = self._halo(send_rep if send_rep.dim() == 3 else send_rep.unsqueeze(0))
+            if rec_rep.dim() == 2:
+                send_rep = send_rep[0]
         self._check_inputs(send_rep, rec_rep, edge_rep)
         names, params = self._param_list()
         three_d, (s3, r3, e3) = self._batchify(send_rep, rec_rep, edge_rep)
@@ -313,7 +320,7 @@ class InteractionNet(nn.Module):
         edge output (nobody reads it), a middle layer may update ``edge_rep`` in place (``first``: the incoming
         tensor belongs to the caller — e.g. the cached static embedding — and is never written).  Same values as
         ``forward``.  Returns ``(node_rep', edge_rep' | None)``."""
-        if not (self.update_edges and self._fusable() and self._is_sorted):
+        if self._halo is not None or not (self.update_edges and self._fusable() and self._is_sorted):
             return self.forward(node_rep, node_rep, edge_rep)
         self._check_inputs(node_rep, node_rep, edge_rep)
         _, (s3, r3, e3) = self._batchify(node_rep, node_rep, edge_rep)
