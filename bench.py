@@ -328,6 +328,93 @@ def step_algorithmic(model, B):
     return nbytes, flops
 
 
+
+def measure_partition(cfg_id, device, rank, world, steps, warmup, math="auto", batch=None):
+    """STRONG-scaling measurement of the node-partitioned rollout (BASELINE.json configs[3] shape by
+    default): ONE batch of forecasts on the whole graph, grid and every mesh level split into `world` contiguous strips,
+    one halo exchange per InteractionNet call — ``halo_push_kernel`` stores boundary rows straight into the peers'
+    symmetric-memory buffers over NVLink, one device barrier, all of it inside the captured CUDA graph.  world == 1 runs
+    the plain model on the same workload (the strong-scaling reference).  Every rank returns the dict (rank 0 prints)."""
+    import torch.distributed as dist
+
+    from neural_lam_b200 import dist as nd
+    from neural_lam_b200 import models, synthetic
+
+    c = CONFIGS[cfg_id]
+    B = batch or c["batch"]
+    spec = synthetic.make_graph_spec(*c["grid"], hierarchical=c["hierarchical"], n_levels=c["n_levels"])
+    ds = synthetic.SyntheticDatastore(spec, d_state=D_STATE, d_forcing=D_FORCING, d_static=D_STATIC, boundary_width=10)
+    cls = models.MODELS[c["model"]]
+    torch.manual_seed(42)
+    if world > 1:
+        model = nd.partition_model(cls, ds, spec, rank, world, hidden_dim=c["hidden"], processor_layers=c["layers"], math=math)
+        lds, sl = model.local_datastore, model.own_grid_slice()
+    else:
+        model = cls(ds, spec, hidden_dim=c["hidden"], processor_layers=c["layers"], math=math)
+        lds, sl = ds, slice(0, ds.num_grid_nodes)
+    fc = models.ARForecaster(model, lds).to(device).eval()
+    G_own = sl.stop - sl.start
+    T = steps + warmup
+    g = torch.Generator().manual_seed(99)
+    init = torch.randn(B, 2, G_own, D_STATE, generator=g).pin_memory()
+    forc = torch.randn(B, T, G_own, D_FORCING, generator=g).pin_memory()
+    bnd = torch.randn(B, T, G_own, D_STATE, generator=g).pin_memory()
+    d_init, d_forc, d_bnd = init.to(device), forc.to(device), bnd.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    with torch.no_grad():
+        bufs = fc.capture(B)
+        fc.set_state(d_init[:, 0], d_init[:, 1])
+
+        def run(t0, n):
+            for i in range(t0, t0 + n):
+                bufs["forcing"].copy_(d_forc[:, i])
+                bufs["boundary"].copy_(d_bnd[:, i])
+                fc.replay_step()
+
+        run(0, warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(warmup, steps)
+        e1.record()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        h_out = torch.empty(B, steps, G_own, D_STATE).pin_memory()
+        fc.rollout_from_host(init, forc[:, :warmup], bnd[:, :warmup])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fc.rollout_from_host(init, forc[:, warmup:], bnd[:, warmup:], out=h_out)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    out = {"workload": c["workload"], "batch": B, "n_gpus": world, "scaling": "strong",
+           "value": B * steps / (dev_ms * 1e-3), "unit": "forecast-steps/s", "ms_per_step": dev_ms / steps,
+           "e2e": {"value": B * steps / (e2e_ms * 1e-3), "unit": "forecast-steps/s",
+                   "h2d_bytes_per_step": B * ds.num_grid_nodes * (D_FORCING + D_STATE) * 4,
+                   "d2h_bytes_per_step": B * ds.num_grid_nodes * D_STATE * 4},
+           "parallelism": ("single GPU, whole graph" if world == 1 else
+                           f"node partition x{world}: grid + every mesh level in {world} strips, halo rows pushed into the "
+                           "peers' symmetric-memory buffers by halo_push_kernel over NVLink, one device barrier per "
+                           "InteractionNet call, captured in the CUDA graph")}
+    if world > 1:
+        sent, recv = model.halo_bytes_per_step(B)
+        out["comm"] = {"halo_exchanges_per_step": len(nd._gnn_edge_sets(model)), "halo_bytes_sent_per_step_rank0": sent,
+                       "halo_bytes_received_per_step_rank0": recv, "transport": type(model.exchanger).__name__}
+    del fc, model, bufs
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -345,6 +432,19 @@ def run_ours(args):
     from neural_lam_b200 import _lib
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    if args.parallelism == "partition":
+        res = measure_partition(args.config, device, rank, world, K, W, args.math, batch=args.batch)
+        if rank == 0:
+            line = {"metric": METRIC, "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": K, "warmup": W,
+                    "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f32 I/O; tf32 tensor-core MLPs, f32 accumulate", "data": "synthetic",
+                    "config": {"workload": res["workload"], "global_batch": res["batch"], "parallelism": res["parallelism"],
+                               "cuda_graph": True}, "e2e": res["e2e"], "comm": res.get("comm")}
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     spec, ds, model, fc = build_model(device, math=args.math)
     G = model.num_grid_nodes
     T = K + W
@@ -411,6 +511,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = t.tolist()
 
+    partition = None
+    if not args.no_partition and args.config == 2:
+        # second measurement of the same run: the node-partitioned rollout (strong scaling) on BASELINE config 4's
+        # shape; at N = 1 this is the unpartitioned reference the N > 1 lines are compared with
+        partition = measure_partition(4, device, rank, world, steps=min(K, 10), warmup=3, math=args.math)
+
     if rank == 0:
         peak, peak_src = _peaks()
         with torch.no_grad():
@@ -475,6 +581,7 @@ def run_ours(args):
                          "traffic": traffic, "algorithmic_bytes": nbytes, "ms_mean": mean_ms, "ms_median": med_ms,
                          "peak_source": peak_src, "l2_flushed": True},
             "step_roofline": step_roof,
+            "partition": partition,
             "cpu_baseline": cpu,
             "ref_cuda": ref_cuda,
             "parity": parity,
@@ -534,12 +641,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-partition", action="store_true", help="skip the node-partition (strong scaling) sub-measurement")
+    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "partition"],
+                    help="replicas: independent forecasts per GPU (weak scaling, the headline line); partition: ONE batch "
+                         "on the node-partitioned graph (strong scaling; --config selects the workload, default 4)")
     ap.add_argument("--cpu-at-scale", action="store_true", help="time the CPU port even for config 4 (minutes)")
     args = ap.parse_args()
     global CFG, METRIC
     CFG = CONFIGS[args.config]
     METRIC = ("forecast-steps/sec (268x238 grid, hidden=64)" if args.config == 2 else
               f"forecast-steps/sec ({CFG['grid'][1]}x{CFG['grid'][0]} grid, hidden={CFG['hidden']}, BASELINE config {args.config})")
+    if args.parallelism == "partition" and args.config == 2 and "--config" not in sys.argv:
+        args.config = 4
+        CFG = CONFIGS[4]
+        METRIC = f"forecast-steps/sec ({CFG['grid'][1]}x{CFG['grid'][0]} grid, hidden={CFG['hidden']}, BASELINE config 4)"
     if not args.batch:
         args.batch = CFG["batch"]
     if args.config == 4:  # the fp64 / fp32 CPU oracle takes minutes per step at 1 M grid nodes
