@@ -67,6 +67,30 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPUs of the NUMA node the GPU hangs
+    off: at 8 ranks the host<->device staging of `e2e` otherwise crosses the socket interconnect.  Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, z = part.partition("-")
+            cpus.update(range(int(a), int(z or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def _bf16_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -426,6 +450,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    numa_node = bind_to_gpu_numa(local_rank) if world > 1 else None
     import __graft_entry__
 
     __graft_entry__.build()
@@ -570,7 +595,7 @@ def run_ours(args):
                        "parallelism": f"replicas x{world} (independent forecasts per GPU, no collective)",
                        "l2": "per-step working set (~0.36 GB x B algorithmic) exceeds the 126 MB L2; "
                              "roofline kernel timed with an explicit 256 MB L2 flush between iterations",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "numa_node_rank0": numa_node},
             "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": "forecast-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step) * K,

@@ -171,6 +171,11 @@ int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, float* ext_l
                    float* const* peer_ext, const int32_t* send_rows, const int32_t* send_ptr,
                    const int32_t* peer_dst_off, int64_t n_send_total, int world, int B, int H, void* stream);
 
+/* Strided host <-> device copy of `height` rows of `width_bytes` (cudaMemcpy2DAsync on `stream`): the per-step slice of a
+ * (B, T, G, F) pinned host tensor in ONE call (ARForecaster.rollout_from_host). */
+int nlam_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                        int host_to_device, void* stream);
+
 /* new_state = bmask * boundary + (1-bmask) * (prev + net_out*diff_std + diff_mean)
  * over (B,G,D); bmask (G), diff_std/mean (D); boundary may be NULL (then bmask ignored). */
 int nlam_step_epilogue(const float* net_out, const float* prev, const float* boundary,

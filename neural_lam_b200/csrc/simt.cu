@@ -485,3 +485,13 @@ extern "C" int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, f
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
 }
+
+// One strided host<->device copy per tensor and forecast step (ARForecaster.rollout_from_host): the step-i slice of a
+// (B, T, G, F) host tensor is B rows of G*F floats with pitch T*G*F — one cudaMemcpy2DAsync instead of B small copies.
+extern "C" int nlam_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
+                                   size_t height, int host_to_device, void* stream) {
+  NLAM_REQUIRE(dst && src, NLAM_E_INVALID, "memcpy2d: null pointer");
+  NLAM_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                                 host_to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return NLAM_OK;
+}

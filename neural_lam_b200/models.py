@@ -17,6 +17,8 @@ is out of scope), the graph comes in as a dict of tensors (``synthetic.make_grap
 is kept receiver-sorted, and input-independent embeddings are cached between steps while the
 weights do not change.
 """
+import ctypes
+
 import torch
 from torch import nn
 
@@ -599,14 +601,28 @@ class ARForecaster(nn.Module):
         out_ready = [torch.cuda.Event() for _ in range(2)]
         out_free = [torch.cuda.Event() for _ in range(2)]
 
+        def copy_step(dev_t, host_t, i, stream, to_device):
+            """step-i slice of a (B, T, G, F) host tensor <-> a dense (B, G, F) device tensor: ONE strided copy"""
+            row = host_t.shape[2] * host_t.shape[3] * 4
+            hp = host_t.data_ptr() + i * row
+            args = (dev_t.data_ptr(), row, hp, host_t.stride(0) * 4) if to_device else (hp, host_t.stride(0) * 4, dev_t.data_ptr(), row)
+            _lib.check(_lib.lib().nlam_memcpy2d_async(*args, row, B, 1 if to_device else 0, ctypes.c_void_p(stream.cuda_stream)))
+
+        dense = all(t.is_contiguous() and t.dtype == torch.float32 and not t.is_cuda
+                    for t in (forcing_features, boundary_states, init_states, out))
+
         def h2d(i):
             k = i & 1
             with torch.cuda.stream(s_in):
                 if i >= 2:
                     s_in.wait_event(in_free[k])
-                for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
-                    io["forc"][k][b].copy_(forcing_features[b, i], non_blocking=True)
-                    io["bnd"][k][b].copy_(boundary_states[b, i], non_blocking=True)
+                if dense:
+                    copy_step(io["forc"][k], forcing_features, i, s_in, True)
+                    copy_step(io["bnd"][k], boundary_states, i, s_in, True)
+                else:
+                    for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
+                        io["forc"][k][b].copy_(forcing_features[b, i], non_blocking=True)
+                        io["bnd"][k][b].copy_(boundary_states[b, i], non_blocking=True)
                 in_ready[k].record(s_in)
 
         for b in range(B):
@@ -629,8 +645,11 @@ class ARForecaster(nn.Module):
             out_ready[k].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(out_ready[k])
-                for b in range(B):
-                    out[b, i].copy_(io["out"][k][b], non_blocking=True)
+                if dense:
+                    copy_step(io["out"][k], out, i, s_out, False)
+                else:
+                    for b in range(B):
+                        out[b, i].copy_(io["out"][k][b], non_blocking=True)
                 out_free[k].record(s_out)
         main.wait_stream(s_out)
         main.wait_stream(s_in)
