@@ -171,6 +171,41 @@ int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, float* ext_l
                    float* const* peer_ext, const int32_t* send_rows, const int32_t* send_ptr,
                    const int32_t* peer_dst_off, int64_t n_send_total, int world, int B, int H, void* stream);
 
+/* ---- Backward building blocks (bwd.cu) and the generic tcgen05 Linear (tc7.cu) -------------------------------
+ * The backward of the path (reference: autograd through gnn_layers.py:110-157 / utils/networks.py:27-40) is composed
+ * from these launches by the host side (neural_lam_b200/backward.py): dX = dY · W and dW = dYᵀ · X run on nlam_linear
+ * (dW as split-K partial products over zero-padded transposes, reduced in a fixed order by nlam_reduce_partials). */
+/* out = epi([x0 | x1] · wᵀ + bias + add0[add0_idx] + add1[add1_idx]); epi = SiLU (act) / LayerNorm (gamma, beta), then
+ * + post[post_idx], optional second output out2 (before the residual), + res.  x0: (B|1, n_rows, k0) with row pitch
+ * x0_pitch (0 = k0); w: (n_out, w_cols) with row pitch ldw, batch stride w_bs (0 = shared).  K multiple of 32, n_out <= 256. */
+int nlam_linear(const float* x0, int64_t x0_bs, int k0, int64_t x0_pitch, const float* x1, int64_t x1_bs, int k1,
+                const float* w, int ldw, int w_cols, int64_t w_bs, const float* bias, int n_out, int act, const float* gamma,
+                const float* beta, float eps, const float* add0, const int32_t* add0_idx, int64_t add0_bs, const float* add1,
+                const int32_t* add1_idx, int64_t add1_bs, const float* post, const int32_t* post_idx, int64_t post_bs,
+                const float* res, int64_t res_bs, int64_t n_rows, int B, float* out, float* out2, void* stream);
+/* out[b, r, :kp] = [s0 | s1 | s2 | s3 | zeros]: the concatenation the reference materialises with torch.cat
+ * (graph/base.py:275-283), zero-padded to kp columns (the generic Linear wants K a multiple of 32) */
+int nlam_pack_rows(const float* s0, const float* s1, const float* s2, const float* s3, int d0, int d1, int d2, int d3,
+                   int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3, float* out, int kp, int64_t n_rows, int B, void* stream);
+/* gh == NULL: out = SiLU(z); else out = gh * SiLU'(z)  (n elements, n % 4 == 0) */
+int nlam_silu(const float* z, const float* gh, float* out, int64_t n, void* stream);
+int nlam_layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out, int64_t rows, int H,
+                       void* stream);
+/* gy = dL/dy for out = LayerNorm(y); dgamma / dbeta (H) overwritten; scratch: nlam_bwd_scratch_floats(H) floats */
+int nlam_layernorm_bwd(const float* g, const float* y, const float* gamma, float eps, float* gy, float* dgamma, float* dbeta,
+                       int64_t rows, int H, float* scratch, void* stream);
+size_t nlam_bwd_scratch_floats(int C);
+/* out[c] = sum_r g[r, c]  (bias gradients); scratch: nlam_bwd_scratch_floats(C) floats */
+int nlam_colsum(const float* g, int64_t rows, int C, float* out, float* scratch, void* stream);
+/* out[r, c] (+)= sum_p part[p, r, c]  (ordered) */
+int nlam_reduce_partials(const float* part, int P, int64_t R, int C, float* out, int64_t out_pitch, int accumulate,
+                         void* stream);
+/* xt[c, r] = x[r, c] (row pitch x_pitch), zero for rows <= r < rows_pad */
+int nlam_transpose_pad(const float* x, int64_t rows, int C, int64_t x_pitch, float* xt, int64_t rows_pad, void* stream);
+/* out[b, e, :] = (a ? a[b, e, :] : 0) + v[b, idx[e], :] * (deg_ptr ? 1 / max(deg(idx[e]), 1) : 1) */
+int nlam_add_gather(const float* a, const float* v, const int32_t* idx, const int32_t* deg_ptr, int64_t n_e, int64_t n_v, int H,
+                    int B, float* out, void* stream);
+
 /* Strided host <-> device copy of `height` rows of `width_bytes` (cudaMemcpy2DAsync on `stream`): the per-step slice of a
  * (B, T, G, F) pinned host tensor in ONE call (ARForecaster.rollout_from_host). */
 int nlam_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,

@@ -77,15 +77,17 @@ struct RowLinProblem {
 int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st);
 // tc7.cu: generic tcgen05 Linear (any K multiple of 32, N <= 256) and the layer paths built from it
 struct LinearCall {
-  const float* x0;      // (B|1, n_rows, k0) dense rows
+  const float* x0;      // (B|1, n_rows, k0) rows; row pitch x0_pitch (0: dense = k0)
   int64_t x0_bs;
   int k0;
+  int64_t x0_pitch;
   const float* x1;      // optional second K block (B|1, n_rows, k1)
   int64_t x1_bs;
   int k1;
   const float* w;       // (n_out, k0 + k1) slice of a row-major matrix with row pitch ldw
   int ldw;
   int w_cols;           // real columns of W (0: k0 + k1); columns past it read as zero (zero-padded inputs)
+  int64_t w_bs;         // batch stride of W in elements (0: one W for every batch; != 0: split-K partial products)
   const float* bias;    // optional (n_out)
   int n_out;
   int act;              // 0 none, 1 SiLU

@@ -31,6 +31,7 @@ struct LinParams {
   long long n_rows;
   int kc0, kc1;      // chunks of source 0 / source 1
   int a_batched[2];
+  int w_batched;
   int n_real;        // real output width (<= N; < N only for direct narrow stores)
   const float* bias;
   int act;           // 0 none, 1 SiLU
@@ -131,7 +132,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_3d(sa, &tmA0, full, kc * KC, tile * 128, p.a_batched[0] ? b : 0, pol_stream);
           else
             tma_load_3d(sa, &tmA1, full, (kc - p.kc0) * KC, tile * 128, p.a_batched[1] ? b : 0, pol_stream);
-          tma_load_3d(sa + A_BYTES, &tmW, full, kc * KC, 0, 0, pol_keep);
+          tma_load_3d(sa + A_BYTES, &tmW, full, kc * KC, 0, p.w_batched ? b : 0, pol_keep);
         }
       }
     }
@@ -282,7 +283,7 @@ static int npad(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 2
 
 bool tc_linear_shape_ok(int k0, int k1, int n_out) {
   if (n_out < 1 || n_out > 256) return false;
-  if (k0 < 32 || k0 % 32 != 0 || k1 % 32 != 0 || k0 + k1 > 1024) return false;
+  if (k0 < 32 || k0 % 32 != 0 || k1 % 32 != 0 || (long long)k0 + k1 > (1LL << 26)) return false;
   return true;
 }
 
@@ -297,8 +298,10 @@ int tc_linear(const LinearCall& c, cudaStream_t st) {
                NLAM_E_INVALID, "tc_linear: pointers must be 16-byte aligned");
   CUtensorMap ma0, ma1, mw;
   const bool b0 = c.x0_bs != 0 && c.B > 1, b1 = c.x1 && c.x1_bs != 0 && c.B > 1;
-  int rc = make_map(&ma0, c.x0, (uint64_t)c.k0, (uint64_t)c.n_rows, b0 ? (uint64_t)c.B : 1, (uint64_t)c.k0,
-                    b0 ? (uint64_t)c.x0_bs : (uint64_t)c.n_rows * c.k0, 128, true);
+  const uint64_t pitch0 = c.x0_pitch ? (uint64_t)c.x0_pitch : (uint64_t)c.k0;
+  NLAM_REQUIRE(pitch0 % 4 == 0 && c.x0_bs % 4 == 0 && c.w_bs % 4 == 0, NLAM_E_INVALID, "tc_linear: pitches must be multiples of 4");
+  int rc = make_map(&ma0, c.x0, (uint64_t)c.k0, (uint64_t)c.n_rows, b0 ? (uint64_t)c.B : 1, pitch0,
+                    b0 ? (uint64_t)c.x0_bs : (uint64_t)c.n_rows * pitch0, 128, true);
   if (rc) return rc;
   if (c.x1) {
     rc = make_map(&ma1, c.x1, (uint64_t)c.k1, (uint64_t)c.n_rows, b1 ? (uint64_t)c.B : 1, (uint64_t)c.k1,
@@ -308,8 +311,9 @@ int tc_linear(const LinearCall& c, cudaStream_t st) {
     ma1 = ma0;
   }
   // W: (n_out rows, k0 + k1 columns) slice of a row-major matrix with row pitch ldw; rows past n_out read as zero
-  rc = make_map(&mw, c.w, (uint64_t)(c.w_cols ? c.w_cols : c.k0 + c.k1), (uint64_t)c.n_out, 1, (uint64_t)c.ldw, (uint64_t)c.n_out * c.ldw, (uint32_t)N,
-                true);
+  const bool wb = c.w_bs != 0 && c.B > 1;
+  rc = make_map(&mw, c.w, (uint64_t)(c.w_cols ? c.w_cols : c.k0 + c.k1), (uint64_t)c.n_out, wb ? (uint64_t)c.B : 1, (uint64_t)c.ldw,
+                wb ? (uint64_t)c.w_bs : (uint64_t)c.n_out * c.ldw, (uint32_t)N, true);
   if (rc) return rc;
   LinParams p;
   memset(&p, 0, sizeof(p));
@@ -320,6 +324,7 @@ int tc_linear(const LinearCall& c, cudaStream_t st) {
   p.kc1 = c.x1 ? c.k1 / KC : 0;
   p.a_batched[0] = b0;
   p.a_batched[1] = b1;
+  p.w_batched = wb;
   p.n_real = c.n_out;
   p.bias = c.bias;
   p.act = c.act;
@@ -508,6 +513,26 @@ int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* o
   c.gamma = m->ln_gamma; c.beta = m->ln_beta; c.eps = m->ln_eps; c.n_rows = n_rows; c.B = B; c.out = out;
   return tc_linear(c, st);
 }
+
+}  // namespace nlam
+// zero-padded concatenation of up to four row blocks: out[b, r, :kp] = [s0 | s1 | s2 | s3 | 0...]
+extern "C" int nlam_pack_rows(const float* s0, const float* s1, const float* s2, const float* s3, int d0, int d1, int d2, int d3,
+                              int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3, float* out, int kp, int64_t n_rows, int B,
+                              void* stream) {
+  NLAM_REQUIRE(s0 && out && kp >= d0 + d1 + d2 + d3 && n_rows >= 0 && B >= 1, NLAM_E_INVALID, "nlam_pack_rows: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * n_rows * kp;
+  if (total == 0) return NLAM_OK;
+  {
+    nlam::ProfScope ps("pack_rows_kernel", st, 8.0 * total);
+    nlam::pack_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+        s0, s1, s2, s3, d0, d1, d2, d3, bs0, bs1, bs2, bs3, out, kp, n_rows, B);
+  }
+  nlam::count_launch();
+  NLAM_CUDA_OK(cudaGetLastError());
+  return NLAM_OK;
+}
+namespace nlam {
 
 // ---- InteractionNet / PropagationNet (reference gnn_layers.py:110-157, :231-249) from the generic Linear kernel ----
 bool tc_inet_gen_supported(const NlamGraph* g, const NlamMlp* em, const NlamMlp* am, int flags, const float* send,

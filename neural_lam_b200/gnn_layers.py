@@ -12,7 +12,7 @@ keys/shapes, full autograd.  CPU tensors raise (no CPU fallback).
 import torch
 from torch import nn
 
-from . import _lib, ops
+from . import _lib, backward, ops
 from .networks import _aten_forward, make_mlp
 
 _DEFAULT_MATH = "auto"
@@ -306,7 +306,23 @@ class InteractionNet(nn.Module):
         def torch_fn(s, r, e, *p):
             return self._torch_forward(names, p, s, r, e)
 
-        outs = ops.run_with_recompute(kernel_fn, torch_fn, [s3, r3, e3, *params])
+        bwd_fn = None
+        if _MATH_FLAGS[self.math or _DEFAULT_MATH] != _lib.MATH_FP32 and backward.inet_supported(self, s3, r3, e3):
+            # TF32 modes: the backward runs on the library's kernels too (backward.py); "fp32" keeps the exact ATen recompute
+            def bwd_fn(saved, gouts, needs=None):
+                s, r, e = saved[:3]
+                g = self._graph(r.device)
+                e_csr = e if self._is_sorted else ops.gather_rows(e, self._perm32)
+                g_rec = gouts[0] if gouts[0] is not None else torch.zeros_like(r)
+                g_eo = gouts[1] if (self.update_edges and len(gouts) > 1 and gouts[1] is not None) else None
+                if g_eo is not None and not self._is_sorted:
+                    g_eo = ops.gather_rows(g_eo.contiguous(), self._perm32)
+                g_s, g_r, g_e, pg = backward.inet_backward(self, g, s, r, e_csr, g_rec.contiguous(), g_eo)
+                if not self._is_sorted:
+                    g_e = ops.gather_rows(g_e, self._inv_perm32)
+                return (g_s, g_r, g_e, *[pg[n] for n in names])
+
+        outs = ops.run_with_recompute(kernel_fn, torch_fn, [s3, r3, e3, *params], bwd_fn=bwd_fn)
         if not three_d:
             outs = [o[0] for o in outs]
         if self.update_edges:

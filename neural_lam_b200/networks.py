@@ -8,7 +8,7 @@ forward path the math runs in libnlam_b200.so (see ``ops.rowmlp`` / ``FusedMLP``
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, backward, ops
 
 
 class FusedMLP(nn.Sequential):
@@ -50,8 +50,20 @@ class FusedMLP(nn.Sequential):
             y = _aten_forward(self, dict(zip(names, p_)), torch.cat(srcs, dim=-1) if n_src > 1 else srcs[0])
             return y if r is None else r + y
 
+        bwd_fn = None
+        if not (self.nlam_flags & _lib.MATH_FP32) and backward.mlp_supported(self, sources, res):
+            def bwd_fn(saved, gouts, needs=None):
+                srcs = list(saved[:n_src])
+                r = saved[n_src] if has_res else None
+                need_src = needs is None or any(needs[:n_src])
+                g_src, g_res, pg = backward.mlp_backward(self, srcs, r, gouts[0].contiguous(), need_src=need_src)
+                g_src = [g if (g is None or g.shape == t.shape) else g.reshape(t.shape) for g, t in zip(g_src, srcs)]
+                if g_res is not None and g_res.shape != r.shape:
+                    g_res = g_res.reshape(r.shape) if g_res.numel() == r.numel() else g_res.sum(0)
+                return (*g_src, *([g_res] if has_res else []), *[pg[n] for n in names])
+
         tensors = [*sources, *([res] if has_res else []), *params]
-        return ops.run_with_recompute(kernel_fn, torch_fn, tensors)
+        return ops.run_with_recompute(kernel_fn, torch_fn, tensors, bwd_fn=bwd_fn)
 
 
 def _aten_forward(seq, params, x):

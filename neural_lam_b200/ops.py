@@ -431,9 +431,33 @@ class RecomputeFn(torch.autograd.Function):
         return (None, None, *res)
 
 
-def run_with_recompute(kernel_fn, torch_fn, tensors):
-    """Kernel forward; if autograd is recording, attach the recompute backward."""
+class KernelBackwardFn(torch.autograd.Function):
+    """Forward = hand-written kernels; backward = hand-written kernels too (``bwd_fn(saved inputs, output grads) ->
+    input grads``, see backward.py).  Nothing but the inputs is saved (recompute-in-backward)."""
+
+    @staticmethod
+    def forward(ctx, kernel_fn, bwd_fn, *tensors):
+        ctx.bwd_fn = bwd_fn
+        ctx.save_for_backward(*tensors)
+        outs = kernel_fn(*tensors)
+        if isinstance(outs, torch.Tensor):
+            return outs
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        needs = ctx.needs_input_grad[2:]
+        with torch.no_grad():
+            grads = ctx.bwd_fn(ctx.saved_tensors, gouts, needs)
+        return (None, None, *[g if n else None for g, n in zip(grads, needs)])
+
+
+def run_with_recompute(kernel_fn, torch_fn, tensors, bwd_fn=None):
+    """Kernel forward; if autograd is recording, attach the backward: the hand-written one (``bwd_fn``) where the shape
+    is covered, else the recompute through a differentiable restatement (``torch_fn``)."""
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        if bwd_fn is not None:
+            return KernelBackwardFn.apply(kernel_fn, bwd_fn, *tensors)
         return RecomputeFn.apply(kernel_fn, torch_fn, *tensors)
     with torch.no_grad():
         return kernel_fn(*tensors)
