@@ -353,6 +353,74 @@ def step_algorithmic(model, B):
 
 
 
+
+def measure_train_step(model, device, B=4, iters=5):
+    """One TRAINING step of the step predictor (forward + backward of a weighted-MSE-like loss; the optimiser step is
+    plain torch AdamW as in the reference, models/module.py:303) at the reference's default batch size 4
+    (train_model.py:261-263): our kernels (tensor-core forward, hand-written backward) next to the reference op sequence
+    under autograd on the same GPU with TF32 matmuls.  Returns a dict (ms per step, samples/s, both arms)."""
+    from oracle import reference_port as rp
+
+    G = model.num_grid_nodes
+    g = torch.Generator().manual_seed(17)
+    prev, pprev = torch.randn(B, G, D_STATE, generator=g).to(device), torch.randn(B, G, D_STATE, generator=g).to(device)
+    forc, tgt = torch.randn(B, G, D_FORCING, generator=g).to(device), torch.randn(B, G, D_STATE, generator=g).to(device)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95))
+
+    def ours():
+        opt.zero_grad(set_to_none=True)
+        pred, _ = model(prev, pprev, forc)
+        ((pred - tgt) ** 2).mean().backward()
+        opt.step()
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / iters
+
+    model.train()
+    ms_ours = timed(ours)
+    model.eval()
+    # reference arm: the oracle op sequence with autograd, parameters as leaf tensors, same optimiser
+    sd = {k: v.detach().clone().to(device) for k, v in model.state_dict().items()}
+    params = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    graph = {}
+    from neural_lam_b200 import models as _m
+
+    for k in ("grid_static_features", "g2m_features", "m2g_features", "g2m_edge_index", "m2g_edge_index", "diff_std", "diff_mean",
+              "m2m_features", "m2m_edge_index", "mesh_static_features", "mesh_up_features", "mesh_up_edge_index",
+              "mesh_down_features", "mesh_down_edge_index"):
+        if hasattr(model, k):
+            v = getattr(model, k)
+            graph[k] = [t.detach() for t in v] if isinstance(v, _m.BufferList) else v.detach()
+    cfg = dict(model=CFG["model"], hidden_layers=1, processor_layers=CFG["layers"], mesh_aggr="sum")
+    ropt = torch.optim.AdamW([p for p in params.values() if p.is_floating_point()], lr=1e-4, betas=(0.9, 0.95))
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+
+    def ref():
+        ropt.zero_grad(set_to_none=True)
+        pred = rp.graph_model_forward(params, graph, cfg, prev, pprev, forc)
+        ((pred - tgt) ** 2).mean().backward()
+        ropt.step()
+
+    try:
+        ms_ref = timed(ref)
+    finally:
+        torch.set_float32_matmul_precision(old)
+    return {"batch": B, "ms_per_step": ms_ours, "value": B / (ms_ours * 1e-3), "unit": "training samples/s",
+            "ref_cuda_ms_per_step": ms_ref, "ref_cuda_value": B / (ms_ref * 1e-3), "speedup": ms_ref / ms_ours,
+            "what": "forward + backward + AdamW step of one forecast step; ours = tcgen05 forward kernels + hand-written "
+                    "backward (backward.py), reference arm = the reference op sequence under torch autograd with TF32 matmuls"}
+
+
 def measure_partition(cfg_id, device, rank, world, steps, warmup, math="auto", batch=None):
     """STRONG-scaling measurement of the node-partitioned rollout (BASELINE.json configs[3] shape by
     default): ONE batch of forecasts on the whole graph, grid and every mesh level split into `world` contiguous strips,
@@ -564,6 +632,10 @@ def run_ours(args):
                      "tensor_peak": tf32_peak, "tensor_peak_source": "0.5 x measured dense bf16 (MEASURED_PEAKS.json); a TF32 "
                      "peak was not measured", "binding": "tensor" if sf / tf32_peak / 1e12 > sb / peak / 1e9 else "hbm"}
         kernels = kernel_table(fc, bufs, peak)
+        train = None
+        if not args.no_train:
+            with torch.enable_grad():
+                train = measure_train_step(model, device)
         parity = None if args.no_parity else parity_check(model, fc, device)
         ref_cuda = None
         if not args.no_ref_cuda:
@@ -607,6 +679,7 @@ def run_ours(args):
                          "peak_source": peak_src, "l2_flushed": True},
             "step_roofline": step_roof,
             "partition": partition,
+            "train": train,
             "cpu_baseline": cpu,
             "ref_cuda": ref_cuda,
             "parity": parity,
@@ -666,6 +739,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (forward + backward) measurement")
     ap.add_argument("--no-partition", action="store_true", help="skip the node-partition (strong scaling) sub-measurement")
     ap.add_argument("--parallelism", default="replicas", choices=["replicas", "partition"],
                     help="replicas: independent forecasts per GPU (weak scaling, the headline line); partition: ONE batch "

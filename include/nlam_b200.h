@@ -187,6 +187,32 @@ int nlam_linear(const float* x0, int64_t x0_bs, int k0, int64_t x0_pitch, const 
  * (graph/base.py:275-283), zero-padded to kp columns (the generic Linear wants K a multiple of 32) */
 int nlam_pack_rows(const float* s0, const float* s1, const float* s2, const float* s3, int d0, int d1, int d2, int d3,
                    int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3, float* out, int kp, int64_t n_rows, int B, void* stream);
+/* Parameter-gradient destinations of one make_mlp network (same layout as NlamMlp; every buffer is OVERWRITTEN). */
+typedef struct NlamMlpGrads {
+  float* w[NLAM_MAX_LINEAR];
+  float* b[NLAM_MAX_LINEAR];
+  float* ln_gamma;
+  float* ln_beta;
+} NlamMlpGrads;
+
+/* Backward of out = mlp(concat_s src_s[b, r, :]) (two Linear layers; residuals pass their gradient through on the host
+ * side): g_out (B, n_rows, n_out) dense -> g_srcs[s] (B, n_rows, dim_s) dense (NULL: not needed) and the parameter
+ * gradients.  Sources may be batch-broadcast (bstride 0).  Replaces autograd through utils/networks.py:27-40. */
+size_t nlam_mlp_bwd_workspace_bytes(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows, int B);
+int nlam_mlp_bwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const float* g_out, float* const* g_srcs,
+                 const NlamMlpGrads* grads, int64_t n_rows, int B, void* workspace, size_t ws_bytes, void* stream);
+
+/* Backward of nlam_inet_fwd (reference: autograd through gnn_layers.py:110-157 / :231-249; tests/test_gnn_layers.py
+ * section F): recompute-in-backward from the layer inputs (edge tensors in CSR order), g_rec_out (B, n_rec, H) and
+ * g_edge_out (B, E, H; NULL if the edge output is unused) -> g_send (B, n_send, H), g_rec, g_edge (dense, per batch
+ * element even for batch-broadcast inputs) and all parameter gradients.  hidden_layers = 1, H in {64, 128, 256};
+ * flags: NLAM_AGGR_MEAN, NLAM_PROPAGATION.  TF32 tensor-core products, ordered reductions (bit-reproducible). */
+size_t nlam_inet_bwd_workspace_bytes(const NlamGraph* g, int B, int H, int flags);
+int nlam_inet_bwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const float* send, int64_t send_bs,
+                  const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, const float* g_rec_out,
+                  const float* g_edge_out, float* g_send, float* g_rec, float* g_edge, const NlamMlpGrads* edge_grads,
+                  const NlamMlpGrads* aggr_grads, int B, int flags, void* workspace, size_t ws_bytes, void* stream);
+
 /* gh == NULL: out = SiLU(z); else out = gh * SiLU'(z)  (n elements, n % 4 == 0) */
 int nlam_silu(const float* z, const float* gh, float* out, int64_t n, void* stream);
 int nlam_layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out, int64_t rows, int H,

@@ -48,6 +48,15 @@ class NlamRowSrc(ctypes.Structure):
     ]
 
 
+class NlamMlpGrads(ctypes.Structure):
+    _fields_ = [
+        ("w", ctypes.c_void_p * NLAM_MAX_LINEAR),
+        ("b", ctypes.c_void_p * NLAM_MAX_LINEAR),
+        ("ln_gamma", ctypes.c_void_p),
+        ("ln_beta", ctypes.c_void_p),
+    ]
+
+
 class NlamError(RuntimeError):
     pass
 
@@ -107,6 +116,17 @@ SYMBOLS = {
                                     ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nlam_pack_rows": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_int64] * 4 +
                        [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
+    "nlam_mlp_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamRowSrc), ctypes.c_int,
+                                                       ctypes.c_int64, ctypes.c_int]),
+    "nlam_mlp_bwd": (ctypes.c_int, [ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamRowSrc), ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(NlamMlpGrads), ctypes.c_int64, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "nlam_inet_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "nlam_inet_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamMlp), ctypes.c_void_p,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.POINTER(NlamMlpGrads), ctypes.POINTER(NlamMlpGrads), ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "nlam_silu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "nlam_layernorm_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     "nlam_layernorm_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),

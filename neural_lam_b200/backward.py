@@ -200,7 +200,7 @@ def mlp_supported(seq, sources, res):
     return all(t.is_cuda and t.dtype == torch.float32 for t in sources)
 
 
-def mlp_backward(seq, sources, res, g_out, need_src=True):
+def mlp_backward_py(seq, sources, res, g_out, need_src=True):
     """Gradients of ``out = (res or 0) + seq(cat(sources, -1))``.  -> ([g_source...], g_res | None, {param name: grad})"""
     lin, ln = _mlp_parts(seq)
     names = {id(p): n for n, p in seq.named_parameters()}
@@ -257,7 +257,7 @@ def inet_supported(layer, send, rec, edge):
             and all(t.is_cuda and t.dtype == torch.float32 for t in (send, rec, edge)))
 
 
-def inet_backward(layer, graph, send, rec, edge_csr, g_rec_out, g_edge_out):
+def inet_backward_py(layer, graph, send, rec, edge_csr, g_rec_out, g_edge_out):
     """Gradients of one InteractionNet / PropagationNet call (inputs (B, n, H), ``edge_csr`` / ``g_edge_out`` in CSR edge
     order; ``g_edge_out`` None when the layer does not update edges or the edge output is unused).
     -> (g_send, g_rec, g_edge_csr, {param name: grad})"""
@@ -336,4 +336,102 @@ def inet_backward(layer, graph, send, rec, edge_csr, g_rec_out, g_edge_out):
         full = torch.zeros((B, Ns_all, H), device=send.device, dtype=torch.float32)
         full[:, :Ns] = g_send
         g_send = full
+    return g_send, g_rec, g_edge, grads
+
+
+# ------------------------------------------------------------------------------------------------ one ABI call per layer
+def _grads_struct(seq, device):
+    """(NlamMlpGrads, {param name: fresh gradient tensor}) for a make_mlp Sequential"""
+    from .ops import mlp_struct  # noqa: F401  (same module order as mlp_struct)
+
+    gs = _lib.NlamMlpGrads()
+    out = {}
+    lin = [(n, m) for n, m in seq.named_children() if isinstance(m, torch.nn.Linear)]
+    lns = [(n, m) for n, m in seq.named_children() if isinstance(m, torch.nn.LayerNorm)]
+    for i, (n, m) in enumerate(lin):
+        out[f"{n}.weight"] = torch.empty_like(m.weight)
+        out[f"{n}.bias"] = torch.empty_like(m.bias)
+        gs.w[i] = out[f"{n}.weight"].data_ptr()
+        gs.b[i] = out[f"{n}.bias"].data_ptr()
+    if lns:
+        n, m = lns[-1]
+        out[f"{n}.weight"] = torch.empty_like(m.weight)
+        out[f"{n}.bias"] = torch.empty_like(m.bias)
+        gs.ln_gamma = out[f"{n}.weight"].data_ptr()
+        gs.ln_beta = out[f"{n}.bias"].data_ptr()
+    return gs, out
+
+
+def mlp_backward(seq, sources, res, g_out, need_src=True):
+    """``nlam_mlp_bwd``: gradients of ``out = (res or 0) + seq(cat(sources, -1))``.
+    -> ([g_source | None ...], g_res | None, {param name: grad})"""
+    from .ops import as_rows, mlp_struct
+
+    L = _lib.lib()
+    prepared = [as_rows(t) for t in sources]
+    B = max(p[1] for p in prepared)
+    n = prepared[0][0].shape[-2]
+    dev = g_out.device
+    g_out = _dense3(g_out)
+    if g_out.shape[0] != B:
+        g_out = g_out.expand(B, -1, -1).contiguous()
+    arr = (_lib.NlamRowSrc * len(prepared))()
+    for i, (t, b, bs) in enumerate(prepared):
+        arr[i].ptr, arr[i].idx, arr[i].bstride, arr[i].dim = t.data_ptr(), None, bs, t.shape[-1]
+    mlp = mlp_struct(seq)
+    gs, pg = _grads_struct(seq, dev)
+    g_src = [torch.empty((B, n, t.shape[-1]), device=dev, dtype=torch.float32) if need_src else None for t, _, _ in prepared]
+    gptr = (ctypes.c_void_p * len(prepared))(*[(g.data_ptr() if g is not None else None) for g in g_src])
+    ws_bytes = L.nlam_mlp_bwd_workspace_bytes(ctypes.byref(mlp), arr, len(prepared), n, B)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.nlam_mlp_bwd(ctypes.byref(mlp), arr, len(prepared), g_out.data_ptr(), gptr, ctypes.byref(gs), n, B,
+                                  ws.data_ptr(), ws_bytes, _sp(g_out)))
+    outs = []
+    for g, orig in zip(g_src, sources):
+        if g is not None and orig.dim() == 2:
+            g = g.sum(0) if B > 1 else g[0]
+        outs.append(g)
+    return outs, (g_out if res is not None else None), pg
+
+
+def inet_backward(layer, graph, send, rec, edge_csr, g_rec_out, g_edge_out):
+    """``nlam_inet_bwd``: gradients of one InteractionNet / PropagationNet call (see ``inet_backward_py`` for the launch
+    sequence).  -> (g_send, g_rec, g_edge_csr, {param name: grad})"""
+    from .ops import as_rows, mlp_struct
+
+    L = _lib.lib()
+    H = layer.input_dim
+    Ns = graph.n_send
+    if send.shape[-2] != Ns:
+        send = send[..., :Ns, :].contiguous()
+    s, Bs, sbs = as_rows(send)
+    r, Br, rbs = as_rows(rec)
+    e, Be, ebs = as_rows(edge_csr)
+    B = max(Bs, Br, Be)
+    if Bs > 1 and sbs not in (0, Ns * H):
+        s, sbs = s.contiguous(), Ns * H
+    if Br > 1 and rbs not in (0, graph.n_rec * H):
+        r, rbs = r.contiguous(), graph.n_rec * H
+    if Be > 1 and ebs not in (0, graph.n_edges * H):
+        e, ebs = e.contiguous(), graph.n_edges * H
+    dev = r.device
+    g_rec_out = _dense3(g_rec_out)
+    g_eo = _dense3(g_edge_out) if g_edge_out is not None else None
+    em, am = mlp_struct(layer.edge_mlp), mlp_struct(layer.aggr_mlp)
+    egs, epg = _grads_struct(layer.edge_mlp, dev)
+    ags, apg = _grads_struct(layer.aggr_mlp, dev)
+    g_send = torch.empty((B, Ns, H), device=dev, dtype=torch.float32)
+    g_rec = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32)
+    g_edge = torch.empty((B, graph.n_edges, H), device=dev, dtype=torch.float32)
+    flags = layer._flags() & (_lib.AGGR_MEAN | _lib.PROPAGATION)
+    ws_bytes = L.nlam_inet_bwd_workspace_bytes(graph.handle, B, H, flags)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.nlam_inet_bwd(graph.handle, ctypes.byref(em), ctypes.byref(am), s.data_ptr(), sbs, r.data_ptr(), rbs,
+                                   e.data_ptr(), ebs, g_rec_out.data_ptr(), g_eo.data_ptr() if g_eo is not None else None,
+                                   g_send.data_ptr(), g_rec.data_ptr(), g_edge.data_ptr(), ctypes.byref(egs), ctypes.byref(ags),
+                                   B, flags, ws.data_ptr(), ws_bytes, _sp(r)))
+    grads = {f"edge_mlp.{k}": v for k, v in epg.items()}
+    grads.update({f"aggr_mlp.{k}": v for k, v in apg.items()})
     return g_send, g_rec, g_edge, grads

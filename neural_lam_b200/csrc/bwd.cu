@@ -167,6 +167,37 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int P, lo
   }
 }
 
+// same sum for FEW outputs and MANY partials (column reductions: thousands of per-warp partial rows, <= 2H columns):
+// block = 32 output elements x 8 slices of the partial range, fixed-order combine through shared memory
+__global__ void reduce_partials_tall_kernel(const float* __restrict__ part, int P, long long total, int C, float* __restrict__ out,
+                                            long long out_pitch, int accumulate) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i < total)
+    for (int p = ty; p < P; p += 8) s += part[(long long)p * total + i];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    const long long r = i / C;
+    float* o = out + r * out_pitch + (i - r * C);
+    *o = accumulate ? *o + t : t;
+  }
+}
+
+static void launch_reduce_partials(const float* part, int P, long long R, int C, float* out, long long out_pitch, int accumulate,
+                                   cudaStream_t st) {
+  const long long total = R * C;
+  if (total <= 8192 && P >= 32)
+    reduce_partials_tall_kernel<<<(int)((total + 31) / 32), 256, 0, st>>>(part, P, total, C, out, out_pitch, accumulate);
+  else
+    reduce_partials_kernel<<<grid_1d(total, 256), 256, 0, st>>>(part, P, R, C, out, out_pitch, accumulate);
+}
+
 // XT[c][r] = X[r][c] for r < rows, 0 for rows <= r < rows_pad   (32 x 32 tiles through shared memory)
 __global__ void transpose_pad_kernel(const float* __restrict__ x, long long rows, int C, long long x_pitch, float* __restrict__ xt,
                                      long long rows_pad) {
@@ -265,7 +296,7 @@ extern "C" int nlam_layernorm_bwd(const float* g, const float* y, const float* g
   }
   count_launch();
   // partials (n_warps, 2H): columns [0,H) -> dgamma, [H,2H) -> dbeta
-  reduce_partials_kernel<<<grid_1d(2 * H, 128), 128, 0, st>>>(scratch, n_warps, 1, 2 * H, scratch + (size_t)n_warps * 2 * H, 2 * H, 0);
+  launch_reduce_partials(scratch, n_warps, 1, 2 * H, scratch + (size_t)n_warps * 2 * H, 2 * H, 0, st);
   count_launch();
   NLAM_CUDA_OK(cudaMemcpyAsync(dgamma, scratch + (size_t)n_warps * 2 * H, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   NLAM_CUDA_OK(cudaMemcpyAsync(dbeta, scratch + (size_t)n_warps * 2 * H + H, H * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -283,7 +314,7 @@ extern "C" int nlam_colsum(const float* g, int64_t rows, int C, float* out, floa
     colsum_kernel<<<grid, 256, 0, st>>>(g, rows, C, scratch);
   }
   count_launch();
-  reduce_partials_kernel<<<grid_1d(C, 128), 128, 0, st>>>(scratch, n_warps, 1, C, out, C, 0);
+  launch_reduce_partials(scratch, n_warps, 1, C, out, C, 0, st);
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
   return NLAM_OK;
@@ -295,7 +326,7 @@ extern "C" int nlam_reduce_partials(const float* part, int P, int64_t R, int C, 
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps("reduce_partials_kernel", st, 4.0 * P * R * C);
-    reduce_partials_kernel<<<grid_1d(R * C, 256), 256, 0, st>>>(part, P, R, C, out, out_pitch, accumulate);
+    launch_reduce_partials(part, P, R, C, out, out_pitch, accumulate, st);
   }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
@@ -348,4 +379,464 @@ extern "C" int nlam_linear(const float* x0, int64_t x0_bs, int k0, int64_t x0_pi
   c.post = post; c.post_idx = post_idx; c.post_bs = post_bs; c.res = res; c.res_bs = res_bs;
   c.n_rows = n_rows; c.B = B; c.out = out; c.out2 = out2;
   return tc_linear(c, (cudaStream_t)stream);
+}
+
+// =====================================================================================================================
+// nlam_mlp_bwd / nlam_inet_bwd: the backward chains composed on the host side of the ABI (one call per layer; all
+// temporaries in the caller's workspace; same sequence of launches as neural_lam_b200/backward.py, which remains as the
+// readable restatement and is tested against this).
+// =====================================================================================================================
+namespace nlam {
+namespace {
+
+struct Arena {  // stack allocator over the caller's workspace; dry = size the workspace without touching memory
+  float* base;
+  size_t off, cap;
+  bool dry;
+  size_t peak = 0;
+  bool overflow = false;
+  float* get(size_t n) {
+    n = (n + 63) / 64 * 64;
+    float* p = dry ? nullptr : base + off;
+    off += n;
+    peak = std::max(peak, off);
+    if (!dry && off > cap) overflow = true;
+    return p;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+  void note() {}
+};
+
+struct Ctx {
+  Arena a;
+  cudaStream_t st;
+  int rc = NLAM_OK;
+  bool ok() const { return rc == NLAM_OK && !a.overflow; }
+};
+
+#define BW_TRY(expr)                  \
+  do {                                \
+    if (!c.a.dry && c.ok()) c.rc = (expr); \
+  } while (0)
+
+// out (B, n, n_out) = epi(x0 (+x1) · w[:, w_off ..]ᵀ ...)
+struct LinArgs {
+  const float* x0 = nullptr; int64_t x0_bs = 0; int k0 = 0; int64_t x0_pitch = 0;
+  const float* x1 = nullptr; int64_t x1_bs = 0; int k1 = 0;
+  const float* w = nullptr; int ldw = 0; int w_cols = 0; int64_t w_bs = 0;
+  const float* bias = nullptr; int n_out = 0;
+  const float* add0 = nullptr; const int32_t* idx0 = nullptr; int64_t add0_bs = 0;
+  const float* add1 = nullptr; const int32_t* idx1 = nullptr; int64_t add1_bs = 0;
+  const float* res = nullptr; int64_t res_bs = 0;
+  int64_t n = 0; int B = 1;
+};
+
+static void lin(Ctx& c, const LinArgs& a, float* out) {
+  if (c.a.dry || !c.ok()) return;
+  LinearCall q;
+  memset(&q, 0, sizeof(q));
+  q.x0 = a.x0; q.x0_bs = a.x0_bs; q.k0 = a.k0; q.x0_pitch = a.x0_pitch; q.x1 = a.x1; q.x1_bs = a.x1_bs; q.k1 = a.k1;
+  q.w = a.w; q.ldw = a.ldw; q.w_cols = a.w_cols; q.w_bs = a.w_bs; q.bias = a.bias; q.n_out = a.n_out;
+  q.add[0] = a.add0; q.add_idx[0] = a.idx0; q.add_bs[0] = a.add0_bs; q.add[1] = a.add1; q.add_idx[1] = a.idx1; q.add_bs[1] = a.add1_bs;
+  q.res = a.res; q.res_bs = a.res_bs; q.n_rows = a.n; q.B = a.B; q.out = out;
+  c.rc = tc_linear(q, c.st);
+}
+
+// xt (C, rows_pad) = transpose of x rows (row r reads x[(r % mod_rows) * pitch + col]); zero padded
+__global__ void transpose_mod_kernel(const float* __restrict__ x, long long rows, long long mod_rows, int C, long long x_pitch,
+                                     float* __restrict__ xt, long long rows_pad) {
+  __shared__ float tile[32][33];
+  const long long tiles_r = (rows_pad + 31) / 32;
+  const int tiles_c = (C + 31) / 32;
+  for (long long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const long long tr = t / tiles_c;
+    const int tc = (int)(t - tr * tiles_c);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+      const long long r = tr * 32 + j;
+      const int col = tc * 32 + tx;
+      tile[j][tx] = (r < rows && col < C) ? x[(mod_rows >= rows ? r : r % mod_rows) * x_pitch + col] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int col = tc * 32 + j;
+      const long long r = tr * 32 + tx;
+      if (col < C && r < rows_pad) xt[(long long)col * rows_pad + r] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+}
+
+static void transpose(Ctx& c, const float* x, int64_t rows, int64_t mod_rows, int C, int64_t pitch, float* xt, int64_t rows_pad) {
+  if (c.a.dry || !c.ok()) return;
+  const long long tiles = ((rows_pad + 31) / 32) * ((C + 31) / 32);
+  {
+    ProfScope ps("transpose_pad_kernel", c.st, 4.0 * C * (rows + rows_pad));
+    transpose_mod_kernel<<<(int)std::min<long long>(tiles, 148 * 16), 256, 0, c.st>>>(x, rows, mod_rows, C, pitch, xt, rows_pad);
+  }
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) c.rc = NLAM_E_CUDA;
+}
+
+// out[:, off .. off+K) (pitch out_pitch) = gyᵀ (R x N, dense) · x (R x K; rows repeat with period x_mod, pitch x_pitch)
+static void grad_weight(Ctx& c, const float* gy, int64_t R, int N, const float* x, int64_t x_mod, int K, int64_t x_pitch,
+                        float* out, int64_t out_pitch) {
+  const int n_tiles = (N + 127) / 128;
+  const int64_t S = std::max<int64_t>(1, std::min<int64_t>(296 / n_tiles, (R + 511) / 512));
+  const int64_t k_per = (((R + S - 1) / S) + 31) / 32 * 32;
+  const int64_t rows_pad = S * k_per;
+  const size_t m = c.a.mark();
+  float* gyT = c.a.get((size_t)N * rows_pad);
+  transpose(c, gy, R, R, N, N, gyT, rows_pad);
+  for (int c0 = 0; c0 < K; c0 += 256) {
+    const int kc = std::min(256, K - c0);
+    const size_t m2 = c.a.mark();
+    float* xT = c.a.get((size_t)kc * rows_pad);
+    float* part = c.a.get((size_t)S * N * kc);
+    c.a.note();
+    transpose(c, x + c0, R, x_mod, kc, x_pitch, xT, rows_pad);
+    LinArgs a;
+    a.x0 = gyT; a.x0_bs = k_per; a.k0 = (int)k_per; a.x0_pitch = rows_pad; a.w = xT; a.ldw = (int)rows_pad; a.w_cols = (int)k_per;
+    a.w_bs = k_per; a.n_out = kc; a.n = N; a.B = (int)S;
+    lin(c, a, part);
+    if (!c.a.dry && c.ok()) c.rc = nlam_reduce_partials(part, (int)S, N, kc, out + c0, out_pitch, 0, c.st);
+    c.a.release(m2);
+  }
+  c.a.release(m);
+}
+
+// out (B, n, n_in) = gy (B, n, N dense) · W[:, w_off .. w_off + n_in)  (+ res dense)
+static void grad_input(Ctx& c, const float* gy, int64_t n, int B, int N, const float* w, int ldw, int n_in, const float* res,
+                       float* out) {
+  const int Np = (N + 31) / 32 * 32, N4 = (N + 3) / 4 * 4;
+  const size_t m = c.a.mark();
+  float* wT = c.a.get((size_t)n_in * N4);
+  transpose(c, w, N, N, n_in, ldw, wT, N4);
+  const float* x0 = gy;
+  if (Np != N) {
+    float* pk = c.a.get((size_t)B * n * Np);
+    if (!c.a.dry && c.ok())
+      c.rc = nlam_pack_rows(gy, nullptr, nullptr, nullptr, N, 0, 0, 0, n * N, 0, 0, 0, pk, Np, n, B, c.st);
+    x0 = pk;
+  }
+  c.a.note();
+  LinArgs a;
+  a.x0 = x0; a.x0_bs = n * Np; a.k0 = Np; a.w = wT; a.ldw = N4; a.w_cols = N; a.n_out = n_in; a.res = res; a.res_bs = n * n_in;
+  a.n = n; a.B = B;
+  lin(c, a, out);
+  c.a.release(m);
+}
+
+static void silu_(Ctx& c, const float* z, const float* gh, float* out, int64_t n) { BW_TRY(nlam_silu(z, gh, out, n, c.st)); }
+static void colsum_(Ctx& c, const float* g, int64_t rows, int C, float* out) {
+  const size_t m = c.a.mark();
+  float* sc = c.a.get(nlam_bwd_scratch_floats(C));
+  c.a.note();
+  BW_TRY(nlam_colsum(g, rows, C, out, sc, c.st));
+  c.a.release(m);
+}
+static void ln_bwd_(Ctx& c, const float* g, const float* y, const float* gamma, float eps, float* gy, float* dgamma, float* dbeta,
+                    int64_t rows, int H) {
+  const size_t m = c.a.mark();
+  float* sc = c.a.get(nlam_bwd_scratch_floats(H));
+  c.a.note();
+  BW_TRY(nlam_layernorm_bwd(g, y, gamma, eps, gy, dgamma, dbeta, rows, H, sc, c.st));
+  c.a.release(m);
+}
+
+struct MlpBwdArgs {
+  const NlamMlp* mlp;
+  const NlamRowSrc* srcs;
+  int n_src;
+  const float* g_out;   // (B, n, n_out) dense
+  float* const* g_srcs; // per source (B, n, dim) dense or NULL
+  const NlamMlpGrads* grads;
+  int64_t n;
+  int B;
+};
+
+static void mlp_bwd_impl(Ctx& c, const MlpBwdArgs& q) {
+  const NlamMlp* m = q.mlp;
+  const int K = m->in_dim, H = m->out_dim[0], no = m->out_dim[1];
+  const int Kp = (K + 31) / 32 * 32, K4 = (K + 3) / 4 * 4;
+  const int64_t n = q.n;
+  const int B = q.B;
+  const int64_t rows = n * B;
+  const size_t mk = c.a.mark();
+  // packed, zero-padded input (B, n, Kp)
+  const float* x = nullptr;
+  int64_t x_bs = 0;
+  if (q.n_src == 1 && K == Kp) {
+    x = q.srcs[0].ptr;
+    x_bs = q.srcs[0].bstride;
+  } else {
+    float* pk = c.a.get((size_t)rows * Kp);
+    const NlamRowSrc* s = q.srcs;
+    if (!c.a.dry && c.ok())
+      c.rc = nlam_pack_rows(s[0].ptr, q.n_src > 1 ? s[1].ptr : nullptr, q.n_src > 2 ? s[2].ptr : nullptr,
+                            q.n_src > 3 ? s[3].ptr : nullptr, s[0].dim, q.n_src > 1 ? s[1].dim : 0, q.n_src > 2 ? s[2].dim : 0,
+                            q.n_src > 3 ? s[3].dim : 0, B > 1 ? s[0].bstride : 0, (q.n_src > 1 && B > 1) ? s[1].bstride : 0,
+                            (q.n_src > 2 && B > 1) ? s[2].bstride : 0, (q.n_src > 3 && B > 1) ? s[3].bstride : 0, pk, Kp, n, B, c.st);
+    x = pk;
+    x_bs = n * Kp;
+  }
+  const float* W1 = m->w[0];
+  int ldw1 = K;
+  if (K % 4) {  // 16-byte row pitch for TMA
+    float* wp = c.a.get((size_t)H * K4);
+    if (!c.a.dry && c.ok()) c.rc = nlam_pack_rows(m->w[0], nullptr, nullptr, nullptr, K, 0, 0, 0, 0, 0, 0, 0, wp, K4, H, 1, c.st);
+    W1 = wp;
+    ldw1 = K4;
+  }
+  float* z = c.a.get((size_t)rows * H);
+  float* h = c.a.get((size_t)rows * H);
+  {
+    LinArgs a;
+    a.x0 = x; a.x0_bs = x_bs; a.k0 = Kp; a.w = W1; a.ldw = ldw1; a.w_cols = K; a.bias = m->b[0]; a.n_out = H; a.n = n; a.B = B;
+    lin(c, a, z);
+  }
+  silu_(c, z, nullptr, h, rows * H);
+  const float* g_y = q.g_out;
+  if (m->ln_gamma) {
+    float* y = c.a.get((size_t)rows * no);
+    float* gy = c.a.get((size_t)rows * no);
+    LinArgs a;
+    a.x0 = h; a.x0_bs = n * H; a.k0 = H; a.w = m->w[1]; a.ldw = H; a.bias = m->b[1]; a.n_out = no; a.n = n; a.B = B;
+    lin(c, a, y);
+    ln_bwd_(c, q.g_out, y, m->ln_gamma, m->ln_eps, gy, q.grads->ln_gamma, q.grads->ln_beta, rows, no);
+    g_y = gy;
+  }
+  colsum_(c, g_y, rows, no, q.grads->b[1]);
+  grad_weight(c, g_y, rows, no, h, rows, H, H, q.grads->w[1], H);
+  float* g_h = c.a.get((size_t)rows * H);
+  grad_input(c, g_y, n, B, no, m->w[1], H, H, nullptr, g_h);
+  silu_(c, z, g_h, g_h, rows * H);  // in place: g_z
+  colsum_(c, g_h, rows, H, q.grads->b[0]);
+  grad_weight(c, g_h, rows, H, x, (x_bs == 0 && B > 1) ? n : rows, K, Kp == K && q.n_src == 1 ? K : Kp, q.grads->w[0], K);
+  bool need_src = false;
+  for (int s = 0; s < q.n_src; ++s) need_src |= q.g_srcs && q.g_srcs[s];
+  if (need_src) {
+    float* gx = c.a.get((size_t)rows * K);
+    grad_input(c, g_h, n, B, H, m->w[0], K, K, nullptr, gx);
+    // split the columns back into the sources (strided device-to-device copies)
+    int col = 0;
+    for (int s = 0; s < q.n_src; ++s) {
+      const int d = q.srcs[s].dim;
+      if (q.g_srcs[s] && !c.a.dry && c.ok()) {
+        if (cudaMemcpy2DAsync(q.g_srcs[s], (size_t)d * 4, gx + col, (size_t)K * 4, (size_t)d * 4, (size_t)rows,
+                              cudaMemcpyDeviceToDevice, c.st) != cudaSuccess)
+          c.rc = NLAM_E_CUDA;
+      }
+      col += d;
+    }
+  }
+  c.a.note();
+  c.a.release(mk);
+}
+
+struct InetBwdArgs {
+  const NlamGraph* g;
+  const NlamMlp* em;
+  const NlamMlp* am;
+  const float* send; int64_t send_bs;
+  const float* rec; int64_t rec_bs;
+  const float* edge; int64_t edge_bs;
+  const float* g_rec_out;
+  const float* g_edge_out;
+  float* g_send; float* g_rec; float* g_edge;
+  const NlamMlpGrads* eg;
+  const NlamMlpGrads* ag;
+  int B;
+  int flags;
+};
+
+static void inet_bwd_impl(Ctx& c, const InetBwdArgs& q) {
+  const NlamGraph* g = q.g;
+  const int H = q.em->out_dim[1], B = q.B;
+  const bool prop = q.flags & NLAM_PROPAGATION;
+  const int mean = (q.flags & (NLAM_AGGR_MEAN | NLAM_PROPAGATION)) ? 1 : 0;
+  const int64_t Ns = g->n_send, Nr = g->n_rec, E = g->n_edges;
+  const int64_t sbs = B > 1 ? q.send_bs : 0, rbs = B > 1 ? q.rec_bs : 0, ebs = B > 1 ? q.edge_bs : 0;
+  const int64_t s_mod = (sbs == 0 && B > 1) ? Ns : Ns * B, r_mod = (rbs == 0 && B > 1) ? Nr : Nr * B,
+                e_mod = (ebs == 0 && B > 1) ? E : E * B;
+  // dense-batch views are required for the transposes (rows of all batches contiguous)
+  const float* W1 = q.em->w[0];
+  const float* W2 = q.em->w[1];
+  const float* Wn1 = q.am->w[0];
+  const float* Wn2 = q.am->w[1];
+  const size_t mk = c.a.mark();
+  float* Ps = c.a.get((size_t)B * Ns * H);
+  float* Pr = c.a.get((size_t)B * Nr * H);
+  float* z1 = c.a.get((size_t)B * E * H);
+  float* h1 = c.a.get((size_t)B * E * H);
+  float* y2 = c.a.get((size_t)B * E * H);
+  float* msg = c.a.get((size_t)B * E * H);
+  float* aggr = c.a.get((size_t)B * Nr * H);
+  float* nz = c.a.get((size_t)B * Nr * H);
+  float* nh = c.a.get((size_t)B * Nr * H);
+  float* ny = c.a.get((size_t)B * Nr * H);
+  float* t_n1 = c.a.get((size_t)B * Nr * H);  // g_ny, later g_Pr
+  float* t_n2 = c.a.get((size_t)B * Nr * H);  // g_nh / g_nz
+  float* g_aggr = c.a.get((size_t)B * Nr * H);
+  float* g_rec0 = c.a.get((size_t)B * Nr * H);
+  float* g_Ps = c.a.get((size_t)B * Ns * H);
+  float* g_sp = prop ? c.a.get((size_t)B * Ns * H) : nullptr;
+  c.a.note();
+  // ---- forward recompute
+  {
+    LinArgs a;
+    a.x0 = q.send; a.x0_bs = sbs; a.k0 = H; a.w = W1 + H; a.ldw = 3 * H; a.n_out = H; a.n = Ns; a.B = B;
+    lin(c, a, Ps);
+    LinArgs b;
+    b.x0 = q.rec; b.x0_bs = rbs; b.k0 = H; b.w = W1 + 2 * H; b.ldw = 3 * H; b.bias = q.em->b[0]; b.n_out = H; b.n = Nr; b.B = B;
+    lin(c, b, Pr);
+    LinArgs e;
+    e.x0 = q.edge; e.x0_bs = ebs; e.k0 = H; e.w = W1; e.ldw = 3 * H; e.n_out = H; e.n = E; e.B = B;
+    e.add0 = Ps; e.idx0 = g->src; e.add0_bs = Ns * H; e.add1 = Pr; e.idx1 = g->dst; e.add1_bs = Nr * H;
+    lin(c, e, z1);
+  }
+  silu_(c, z1, nullptr, h1, (int64_t)B * E * H);
+  {
+    LinArgs a;
+    a.x0 = h1; a.x0_bs = E * H; a.k0 = H; a.w = W2; a.ldw = H; a.bias = q.em->b[1]; a.n_out = H; a.n = E; a.B = B;
+    lin(c, a, y2);
+  }
+  BW_TRY(nlam_layernorm_fwd(y2, q.em->ln_gamma, q.em->ln_beta, q.em->ln_eps, msg, (int64_t)B * E, H, c.st));
+  if (prop) {
+    // m += x_j: gather of the (dense-batch) sender rows
+    if (sbs == 0 && B > 1) {
+      for (int b = 0; b < B; ++b)
+        BW_TRY(nlam_add_gather(msg + (size_t)b * E * H, q.send, g->src, nullptr, E, Ns, H, 1, msg + (size_t)b * E * H, c.st));
+    } else {
+      BW_TRY(nlam_add_gather(msg, q.send, g->src, nullptr, E, Ns, H, B, msg, c.st));
+    }
+  }
+  BW_TRY(nlam_segment_sum(g->rowptr, nullptr, Nr, msg, E * H, aggr, Nr * H, B, H, mean, c.st));
+  {
+    LinArgs a;
+    a.x0 = q.rec; a.x0_bs = rbs; a.k0 = H; a.x1 = aggr; a.x1_bs = Nr * H; a.k1 = H; a.w = Wn1; a.ldw = 2 * H; a.bias = q.am->b[0];
+    a.n_out = H; a.n = Nr; a.B = B;
+    lin(c, a, nz);
+  }
+  silu_(c, nz, nullptr, nh, (int64_t)B * Nr * H);
+  {
+    LinArgs a;
+    a.x0 = nh; a.x0_bs = Nr * H; a.k0 = H; a.w = Wn2; a.ldw = H; a.bias = q.am->b[1]; a.n_out = H; a.n = Nr; a.B = B;
+    lin(c, a, ny);
+  }
+  // ---- node update backward
+  ln_bwd_(c, q.g_rec_out, ny, q.am->ln_gamma, q.am->ln_eps, t_n1, q.ag->ln_gamma, q.ag->ln_beta, (int64_t)B * Nr, H);
+  colsum_(c, t_n1, (int64_t)B * Nr, H, q.ag->b[1]);
+  grad_weight(c, t_n1, (int64_t)B * Nr, H, nh, (int64_t)B * Nr, H, H, q.ag->w[1], H);
+  grad_input(c, t_n1, Nr, B, H, Wn2, H, H, nullptr, t_n2);
+  silu_(c, nz, t_n2, t_n2, (int64_t)B * Nr * H);  // g_nz
+  colsum_(c, t_n2, (int64_t)B * Nr, H, q.ag->b[0]);
+  grad_weight(c, t_n2, (int64_t)B * Nr, H, q.rec, r_mod, H, H, q.ag->w[0], 2 * H);
+  grad_weight(c, t_n2, (int64_t)B * Nr, H, aggr, (int64_t)B * Nr, H, H, q.ag->w[0] + H, 2 * H);
+  grad_input(c, t_n2, Nr, B, H, Wn1, 2 * H, H, prop ? nullptr : q.g_rec_out, g_rec0);
+  grad_input(c, t_n2, Nr, B, H, Wn1 + H, 2 * H, H, prop ? q.g_rec_out : nullptr, g_aggr);
+  // ---- message gradient and the edge MLP
+  float* g_m = msg;  // the messages themselves are no longer needed
+  BW_TRY(nlam_add_gather(q.g_edge_out, g_aggr, g->dst, mean ? g->rowptr : nullptr, E, Nr, H, B, g_m, c.st));
+  float* g_y2 = c.a.get((size_t)B * E * H);
+  c.a.note();
+  ln_bwd_(c, g_m, y2, q.em->ln_gamma, q.em->ln_eps, g_y2, q.eg->ln_gamma, q.eg->ln_beta, (int64_t)B * E, H);
+  if (prop) BW_TRY(nlam_segment_sum(g->sptr, g->sperm, Ns, g_m, E * H, g_sp, Ns * H, B, H, 0, c.st));
+  colsum_(c, g_y2, (int64_t)B * E, H, q.eg->b[1]);
+  grad_weight(c, g_y2, (int64_t)B * E, H, h1, (int64_t)B * E, H, H, q.eg->w[1], H);
+  float* g_z1 = y2;  // y2 is dead once g_y2 exists
+  grad_input(c, g_y2, E, B, H, W2, H, H, nullptr, g_z1);
+  silu_(c, z1, g_z1, g_z1, (int64_t)B * E * H);
+  grad_weight(c, g_z1, (int64_t)B * E, H, q.edge, e_mod, H, H, q.eg->w[0], 3 * H);
+  grad_input(c, g_z1, E, B, H, W1, 3 * H, H, q.g_edge_out, q.g_edge);
+  BW_TRY(nlam_segment_sum(g->sptr, g->sperm, Ns, g_z1, E * H, g_Ps, Ns * H, B, H, 0, c.st));
+  float* g_Pr = t_n1;
+  BW_TRY(nlam_segment_sum(g->rowptr, nullptr, Nr, g_z1, E * H, g_Pr, Nr * H, B, H, 0, c.st));
+  colsum_(c, g_Pr, (int64_t)B * Nr, H, q.eg->b[0]);
+  grad_weight(c, g_Ps, (int64_t)B * Ns, H, q.send, s_mod, H, H, q.eg->w[0] + H, 3 * H);
+  grad_weight(c, g_Pr, (int64_t)B * Nr, H, q.rec, r_mod, H, H, q.eg->w[0] + 2 * H, 3 * H);
+  grad_input(c, g_Ps, Ns, B, H, W1 + H, 3 * H, H, g_sp, q.g_send);
+  grad_input(c, g_Pr, Nr, B, H, W1 + 2 * H, 3 * H, H, g_rec0, q.g_rec);
+  c.a.note();
+  c.a.release(mk);
+}
+
+}  // namespace
+}  // namespace nlam
+
+static bool bwd_shapes_ok(const NlamMlp* m) {
+  if (!m || m->n_linear != 2) return false;
+  const int H = m->out_dim[0], no = m->out_dim[1];
+  return H % 32 == 0 && H <= 256 && no >= 1 && no <= 256 && (!m->ln_gamma || no == 32 || no == 64 || no == 128 || no == 256);
+}
+
+extern "C" size_t nlam_mlp_bwd_workspace_bytes(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows, int B) {
+  if (!bwd_shapes_ok(mlp) || !srcs || n_src < 1 || n_src > 4) return 0;
+  Ctx c;
+  c.a = Arena{nullptr, 0, 0, true};
+  c.st = nullptr;
+  NlamMlpGrads dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  float* gs[4] = {(float*)16, (float*)16, (float*)16, (float*)16};
+  MlpBwdArgs q{mlp, srcs, n_src, nullptr, gs, &dummy, n_rows, B};
+  mlp_bwd_impl(c, q);
+  return (c.a.peak + 64) * sizeof(float);
+}
+
+extern "C" int nlam_mlp_bwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const float* g_out, float* const* g_srcs,
+                            const NlamMlpGrads* grads, int64_t n_rows, int B, void* workspace, size_t ws_bytes, void* stream) {
+  NLAM_REQUIRE(mlp && srcs && g_out && grads && workspace && n_src >= 1 && n_src <= 4, NLAM_E_INVALID, "nlam_mlp_bwd: null argument");
+  NLAM_REQUIRE(bwd_shapes_ok(mlp), NLAM_E_UNSUPPORTED, "nlam_mlp_bwd: MLP shape not covered (two Linear layers, hidden width a multiple of 32 <= 256)");
+  for (int s = 0; s < n_src; ++s) NLAM_REQUIRE(!srcs[s].idx, NLAM_E_UNSUPPORTED, "nlam_mlp_bwd: gathered sources unsupported");
+  NLAM_REQUIRE(ws_bytes >= nlam_mlp_bwd_workspace_bytes(mlp, srcs, n_src, n_rows, B), NLAM_E_WORKSPACE, "nlam_mlp_bwd: workspace too small");
+  Ctx c;
+  c.a = Arena{(float*)workspace, 0, ws_bytes / sizeof(float), false};
+  c.st = (cudaStream_t)stream;
+  MlpBwdArgs q{mlp, srcs, n_src, g_out, g_srcs, grads, n_rows, B};
+  mlp_bwd_impl(c, q);
+  NLAM_REQUIRE(!c.a.overflow, NLAM_E_WORKSPACE, "nlam_mlp_bwd: workspace overflow");
+  return c.rc;
+}
+
+extern "C" size_t nlam_inet_bwd_workspace_bytes(const NlamGraph* g, int B, int H, int flags) {
+  if (!g) return 0;
+  Ctx c;
+  c.a = Arena{nullptr, 0, 0, true};
+  c.st = nullptr;
+  NlamMlp em, am;
+  memset(&em, 0, sizeof(em));
+  memset(&am, 0, sizeof(am));
+  em.n_linear = am.n_linear = 2;
+  em.in_dim = 3 * H; am.in_dim = 2 * H;
+  em.out_dim[0] = em.out_dim[1] = am.out_dim[0] = am.out_dim[1] = H;
+  NlamMlpGrads d;
+  memset(&d, 0, sizeof(d));
+  InetBwdArgs q{g, &em, &am, nullptr, 1, nullptr, 1, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr, &d, &d, B, flags};
+  inet_bwd_impl(c, q);
+  return (c.a.peak + 64) * sizeof(float);
+}
+
+extern "C" int nlam_inet_bwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const float* send,
+                             int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs,
+                             const float* g_rec_out, const float* g_edge_out, float* g_send, float* g_rec, float* g_edge,
+                             const NlamMlpGrads* edge_grads, const NlamMlpGrads* aggr_grads, int B, int flags, void* workspace,
+                             size_t ws_bytes, void* stream) {
+  NLAM_REQUIRE(g && edge_mlp && aggr_mlp && send && rec && edge && g_rec_out && g_send && g_rec && g_edge && edge_grads &&
+                   aggr_grads && workspace,
+               NLAM_E_INVALID, "nlam_inet_bwd: null argument");
+  const int H = edge_mlp->out_dim[1];
+  NLAM_REQUIRE(bwd_shapes_ok(edge_mlp) && bwd_shapes_ok(aggr_mlp) && edge_mlp->ln_gamma && aggr_mlp->ln_gamma &&
+                   (H == 64 || H == 128 || H == 256) && edge_mlp->in_dim == 3 * H && aggr_mlp->in_dim == 2 * H &&
+                   edge_mlp->out_dim[0] == H && aggr_mlp->out_dim[0] == H && aggr_mlp->out_dim[1] == H,
+               NLAM_E_UNSUPPORTED, "nlam_inet_bwd: layer shape not covered (hidden_layers = 1, H in {64, 128, 256})");
+  NLAM_REQUIRE(ws_bytes >= nlam_inet_bwd_workspace_bytes(g, B, H, flags), NLAM_E_WORKSPACE, "nlam_inet_bwd: workspace too small");
+  Ctx c;
+  c.a = Arena{(float*)workspace, 0, ws_bytes / sizeof(float), false};
+  c.st = (cudaStream_t)stream;
+  InetBwdArgs q{g, edge_mlp, aggr_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, g_rec_out, g_edge_out, g_send, g_rec, g_edge,
+                edge_grads, aggr_grads, B, flags};
+  inet_bwd_impl(c, q);
+  NLAM_REQUIRE(!c.a.overflow, NLAM_E_WORKSPACE, "nlam_inet_bwd: workspace overflow");
+  return c.rc;
 }

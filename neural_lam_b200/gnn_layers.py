@@ -318,6 +318,10 @@ class InteractionNet(nn.Module):
                 if g_eo is not None and not self._is_sorted:
                     g_eo = ops.gather_rows(g_eo.contiguous(), self._perm32)
                 g_s, g_r, g_e, pg = backward.inet_backward(self, g, s, r, e_csr, g_rec.contiguous(), g_eo)
+                if g_s.shape[1] != s.shape[1]:  # sender rows no edge references
+                    pad = torch.zeros((g_s.shape[0], s.shape[1], g_s.shape[2]), device=g_s.device, dtype=g_s.dtype)
+                    pad[:, : g_s.shape[1]] = g_s
+                    g_s = pad
                 if not self._is_sorted:
                     g_e = ops.gather_rows(g_e, self._inv_perm32)
                 return (g_s, g_r, g_e, *[pg[n] for n in names])

@@ -196,3 +196,39 @@ def test_graphlam_training_step_on_kernel_backward():
         assert p.grad is not None, k
         worst = max(worst, _close(k, p.grad, p64[k].grad, rel=3e-2, abs_=2e-4))
     print(f"GraphLAM training step: max relative gradient error {worst:.3e}")
+
+
+def test_abi_backward_chain_equals_host_composition():
+    """``nlam_inet_bwd`` / ``nlam_mlp_bwd`` (one ABI call per layer, temporaries in a caller-provided workspace) launch
+    the same kernels in the same order as the host-side compositions of backward.py: bit-identical gradients."""
+    from neural_lam_b200 import backward
+
+    g = torch.Generator().manual_seed(2)
+    ns, nr, ne, H, B = 180, 120, 1000, 64, 2
+    ei = torch.stack([torch.randint(0, ns, (ne,), generator=g), torch.randint(0, nr, (ne,), generator=g)])
+    ei[1, -1] = nr - 1
+    ei = ei[:, torch.sort(ei[1], stable=True).indices]
+    for cls, aggr, upd in ((nlb.InteractionNet, "mean", True), (nlb.PropagationNet, "sum", False)):
+        torch.manual_seed(0)
+        net = cls(ei, H, update_edges=upd, aggr=aggr).to(DEV)
+        send, rec = torch.randn(B, ns, H, device=DEV), torch.randn(nr, H, device=DEV).unsqueeze(0).expand(B, -1, -1)
+        edge = torch.randn(B, ne, H, device=DEV)
+        g_rec, g_edge = torch.randn(B, nr, H, device=DEV), (torch.randn(B, ne, H, device=DEV) if upd else None)
+        graph = net._graph(send.device)
+        a = backward.inet_backward(net, graph, send, rec, edge, g_rec, g_edge)
+        b = backward.inet_backward_py(net, graph, send, rec, edge, g_rec, g_edge)
+        for x, y in zip(a[:3], b[:3]):
+            torch.testing.assert_close(x, y, rtol=0, atol=0)
+        assert set(a[3]) == set(b[3])
+        for k in a[3]:
+            torch.testing.assert_close(a[3][k], b[3][k], rtol=0, atol=0)
+    mlp = nlb.make_mlp([56, 64, 17], layer_norm=False).to(DEV)
+    srcs = [torch.randn(2, 300, 17, device=DEV), torch.randn(2, 300, 17, device=DEV), torch.randn(2, 300, 18, device=DEV),
+            torch.randn(300, 4, device=DEV)]
+    go = torch.randn(2, 300, 17, device=DEV)
+    a = backward.mlp_backward(mlp, srcs, None, go)
+    b = backward.mlp_backward_py(mlp, srcs, None, go)
+    for x, y in zip(a[0], b[0]):
+        torch.testing.assert_close(x, y.contiguous(), rtol=0, atol=0)
+    for k in a[2]:
+        torch.testing.assert_close(a[2][k], b[2][k], rtol=0, atol=0)
