@@ -243,6 +243,14 @@ int nlam_step_epilogue(const float* net_out, const float* prev, const float* bou
                        const float* bmask, const float* diff_std, const float* diff_mean,
                        float* new_state, int64_t B, int64_t G, int64_t D, void* stream);
 
+/* The same with the reference's CLAMPED update for state variables with configured limits (models/step_predictors/
+ * base.py:296-396): clamp_kind[d] = 0 plain residual, 1 sigmoid between (clamp_lo[d], clamp_up[d]), 2 softplus above
+ * clamp_lo[d], 3 mirrored softplus below clamp_up[d]; new = f(f^-1(prev) + net_out*diff_std + diff_mean), then the
+ * boundary mix.  Limits in standardised units. */
+int nlam_step_epilogue_clamped(const float* net_out, const float* prev, const float* boundary, const float* bmask,
+                               const float* diff_std, const float* diff_mean, const int32_t* clamp_kind, const float* clamp_lo,
+                               const float* clamp_up, float* new_state, int64_t B, int64_t G, int64_t D, void* stream);
+
 /* output_map + step epilogue in one launch (reference graph/base.py:322-342 followed by
  * forecasters/autoregressive.py:128-131):
  *   y = MLP(concat_s src_s[b, r, :])                      (narrow output D < 64, no LayerNorm)

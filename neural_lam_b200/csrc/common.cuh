@@ -60,9 +60,6 @@ struct StepEpilogue {  // fused forecast-step epilogue of a narrow-output row ML
 bool tc_edge2_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, const float* send, int64_t send_bs,
                         const float* rec, int64_t rec_bs, int B, int64_t send_rows);
 size_t tc_edge2_workspace_floats(const NlamGraph* g, int B, int64_t send_rows_max);
-int tc_edge2(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
-             int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-             cudaStream_t stream, int64_t send_rows, float* ws);
 // tc2.cu: out = x · wsliceᵀ (+ bias) for 64-wide rows; wslice = 64 columns of a row-major weight with row pitch ldw
 struct RowLinProblem {
   const float* x;
@@ -128,7 +125,6 @@ size_t tc_edge_bcast_workspace_floats(const NlamGraph* g, int B, int64_t rec_bs)
 int tc_edge_bcast(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
                   int64_t rec_bs, const float* edge, float* aggr_out, int B, int flags, cudaStream_t st, float* ws);
 // tc5.cu
-bool tc_edge3_enabled();
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, float* ws);

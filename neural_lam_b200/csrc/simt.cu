@@ -367,6 +367,50 @@ __global__ void step_epilogue_kernel(const float* __restrict__ net_out, const fl
   }
 }
 
+// Clamped state update (reference models/step_predictors/base.py:296-334, :366-396; utils/tensor.py:7-81): per state
+// variable kind 0 = plain residual, 1 = scaled sigmoid between (lo, up), 2 = softplus above lo, 3 = mirrored softplus
+// below up; X' = f(f^-1(X) + delta), sharpness 1, centre 0, softplus threshold 20 and the reference's clamps of the
+// inverse functions.
+__device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float inv_softplus(float y) {
+  const float yc = fminf(fmaxf(y, 9.5367386e-07f), 20.f);  // float32(log(1 + 1e-6)), threshold 20
+  return y <= 20.f ? logf(expm1f(yc)) : y;
+}
+
+__global__ void step_epilogue_clamped_kernel(const float* __restrict__ net_out, const float* __restrict__ prev,
+                                             const float* __restrict__ boundary, const float* __restrict__ bmask,
+                                             const float* __restrict__ dstd, const float* __restrict__ dmean,
+                                             const int32_t* __restrict__ kind, const float* __restrict__ lo,
+                                             const float* __restrict__ up, float* __restrict__ new_state, long long B,
+                                             long long G, long long D) {
+  const long long total = B * G * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long gidx = (i / D) % G;
+    const float x = prev[i];
+    const float delta = net_out[i] * dstd[d] + dmean[d];
+    float pred;
+    const int k = kind[d];
+    if (k == 1) {
+      const float a = lo[d], w = up[d] - lo[d];
+      const float xc = fminf(fmaxf((x - a) / w, 1e-6f), 1.f - 1e-6f);
+      const float z = logf(xc / (1.f - xc)) + delta;
+      pred = a + w * (1.f / (1.f + expf(-z)));
+    } else if (k == 2) {
+      pred = lo[d] + softplus20(inv_softplus(x - lo[d]) + delta);
+    } else if (k == 3) {
+      pred = up[d] - softplus20(inv_softplus(up[d] - x) - delta);
+    } else {
+      pred = x + delta;
+    }
+    if (boundary) {
+      const float m = bmask[gidx];
+      pred = m * boundary[i] + (1.0f - m) * pred;
+    }
+    new_state[i] = pred;
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   return (int)std::max<long long>(1, std::min<long long>(g, 148LL * 16));
@@ -429,6 +473,25 @@ extern "C" int nlam_step_epilogue(const float* net_out, const float* prev, const
     ProfScope ps("step_epilogue_kernel", (cudaStream_t)stream, 4.0 * total * (boundary ? 4 : 3));
     step_epilogue_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(net_out, prev, boundary, bmask, diff_std,
                                                                                  diff_mean, new_state, B, G, D);
+  }
+  count_launch();
+  NLAM_CUDA_OK(cudaGetLastError());
+  return NLAM_OK;
+}
+
+extern "C" int nlam_step_epilogue_clamped(const float* net_out, const float* prev, const float* boundary, const float* bmask,
+                                          const float* diff_std, const float* diff_mean, const int32_t* clamp_kind,
+                                          const float* clamp_lo, const float* clamp_up, float* new_state, int64_t B, int64_t G,
+                                          int64_t D, void* stream) {
+  NLAM_REQUIRE(net_out && prev && diff_std && diff_mean && new_state && clamp_kind && clamp_lo && clamp_up, NLAM_E_INVALID,
+               "step_epilogue_clamped: null argument");
+  NLAM_REQUIRE((boundary == nullptr) || bmask, NLAM_E_INVALID, "step_epilogue_clamped: boundary without mask");
+  long long total = B * G * D;
+  if (total == 0) return NLAM_OK;
+  {
+    ProfScope ps("step_epilogue_clamped_kernel", (cudaStream_t)stream, 4.0 * total * (boundary ? 4 : 3));
+    step_epilogue_clamped_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        net_out, prev, boundary, bmask, diff_std, diff_mean, clamp_kind, clamp_lo, clamp_up, new_state, B, G, D);
   }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());

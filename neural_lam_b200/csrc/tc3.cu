@@ -24,22 +24,6 @@
 
 namespace nlam {
 
-namespace e3 {
-constexpr int THREADS = 640;
-constexpr int G2_THREADS = 256;
-constexpr int E1_THREADS = 128;
-constexpr int LD_THREADS = 96;
-constexpr int W_E1 = 8, W_MMA = 16, W_LD = 17;
-constexpr uint32_t BLK = 16384;
-constexpr uint32_t WBLK = 8192;
-constexpr uint32_t OFF_W1E = 0;
-constexpr uint32_t OFF_W1R = 2 * WBLK;
-constexpr uint32_t OFF_W2 = 4 * WBLK;
-constexpr uint32_t OFF_REC = 6 * WBLK;             // receiver tile (2 blocks)
-constexpr uint32_t OFF_ST = OFF_REC + 2 * BLK;     // stage s: [e0 e1 ps0 ps1]
-constexpr uint32_t OFF_MISC = OFF_ST + 2 * 4 * BLK;
-constexpr uint32_t SMEM = OFF_MISC + 2048;
-}  // namespace e3
 
 struct EllParams {
   const int32_t* src;   // CSR-ordered sender ids (E = d * n_rec)
@@ -80,337 +64,6 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
                : "memory");
 }
 
-__global__ void __launch_bounds__(e3::THREADS, 1)
-tc_ell_edge_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmRec,
-                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                   const __grid_constant__ CUtensorMap tmPs, const EllParams p) {
-  using namespace e3;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if ((sbase & 1023u) != 0) {
-    if (tid == 0) printf("nlam tc_ell: dynamic shared memory not 1024-byte aligned\n");
-    __trap();
-  }
-  const uint32_t mb = sbase + OFF_MISC;
-  const uint32_t bar_w = mb + 0;
-  const uint32_t bar_rec_full = mb + 8;   // receiver tile landed (1 + 32 KB tx)
-  const uint32_t bar_rec_free = mb + 16;  // ... and consumed by the D_r GEMM
-  const uint32_t bar_full = mb + 24;      // [2] sub-tile stage filled (1 + 64 KB tx)
-  const uint32_t bar_dr_full = mb + 40;   // [2] D_r ready (per tile parity)
-  const uint32_t bar_d1_full = mb + 56;   // [2]
-  const uint32_t bar_hb_full = mb + 72;   // [2] hidden written by epilogue 1 (128 arrivals) = stage released
-  const uint32_t bar_d2_full = mb + 88;   // [2]
-  const uint32_t bar_d_free = mb + 104;   // [2] D2 drained (256 arrivals)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 120);
-  float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 128);  // b1 | b2 | gamma | beta
-
-  if (warp == W_MMA) {
-    if (lane == 0) {
-      mbar_init(bar_w, 1);
-      mbar_init(bar_rec_full, 1);
-      mbar_init(bar_rec_free, 1);
-      for (int t = 0; t < 2; ++t) {
-        mbar_init(bar_full + 8 * t, 1);
-        mbar_init(bar_dr_full + 8 * t, 1);
-        mbar_init(bar_d1_full + 8 * t, 1);
-        mbar_init(bar_hb_full + 8 * t, E1_THREADS);
-        mbar_init(bar_d2_full + 8 * t, 1);
-        mbar_init(bar_d_free + 8 * t, G2_THREADS);
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp == W_LD && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmE) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmRec) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
-  }
-  if (tid < 64) {
-    sprm[tid] = p.b1[tid];
-    sprm[64 + tid] = p.b2[tid];
-    sprm[128 + tid] = p.gamma[tid];
-    sprm[192 + tid] = p.beta[tid];
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns: D_r[tp] at tp*64 (tp = tile parity); sub-tile stage ts: D at 128 + ts*128, hidden at +64;
-  // LayerNorm scratch at 384.
-  const int d = p.d;
-  const int n_work = p.n_tiles * p.B;  // receiver tiles
-  int n_my = 0;
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) ++n_my;
-  const int n_sub = n_my * d;  // sub-tiles of this CTA, j = ti*d + k
-
-  if (warp >= W_LD) {
-    // =============================== loaders (3 warps) ===============================
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_keep = policy_evict_last();
-    const int lw = warp - W_LD;
-    if (lw == 0 && lane == 0) {
-      mbar_expect_tx(bar_w, 6u * WBLK);
-      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W1E + j * WBLK, &tmW1, bar_w, 32 * j, 0);        // e columns
-      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W1R + j * WBLK, &tmW1, bar_w, 128 + 32 * j, 0);  // receiver columns
-      for (int j = 0; j < 2; ++j) tma_load_2d(sbase + OFF_W2 + j * WBLK, &tmW2, bar_w, 32 * j, 0);
-    }
-    // lanes 0-21 of loader warp lw issue gather4 op = lw*22 + lane (< 64): row group op&31, column block op>>5
-    const int op = lw * 22 + lane;
-    const int grp4 = op & 31, jb = (op >> 5) & 1;
-    const bool issuer = lane < 22 && op < 64;
-    int j = 0;
-    for (int ti = 0; ti < n_my; ++ti) {
-      const int w = blockIdx.x + ti * gridDim.x;
-      const int b = w / p.n_tiles, t = w - b * p.n_tiles;
-      const int r0 = t * 128;
-      if (lw == 0 && lane == 0) {
-        mbar_wait(bar_rec_free, (uint32_t)((ti & 1) ^ 1));  // D_r GEMM of the previous tile has read the buffer
-        mbar_expect_tx(bar_rec_full, 2u * BLK);
-        tma_load_3d(sbase + OFF_REC, &tmRec, bar_rec_full, 0, r0, p.rec_batched ? b : 0, pol_stream);
-        tma_load_3d(sbase + OFF_REC + BLK, &tmRec, bar_rec_full, 32, r0, p.rec_batched ? b : 0, pol_stream);
-      }
-      for (int k = 0; k < d; ++k, ++j) {
-        const int s = j & 1;
-        const uint32_t full = bar_full + 8 * s;
-        const uint32_t stg = sbase + OFF_ST + s * 4 * BLK;
-        // sender ids of window rows 4*grp4 .. +3 for neighbour slot k (rows past the end gather row 0)
-        int idx[4] = {0, 0, 0, 0};
-        if (issuer) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const long long r = (long long)r0 + 4 * grp4 + u;
-            idx[u] = (r < p.n_rec) ? __ldg(p.src + r * d + k) : 0;
-          }
-        }
-        if (lw == 0) {
-          if (lane == 0) {
-            mbar_wait(bar_hb_full + 8 * s, (uint32_t)(((j >> 1) & 1) ^ 1));  // epilogue 1 of sub-tile j-2 released it
-            E3_DBG(0, j);
-            mbar_expect_tx(full, 4u * BLK);
-            tma_load_4d(stg, &tmE, full, 0, k, r0, p.e_batched ? b : 0, pol_stream);
-            tma_load_4d(stg + BLK, &tmE, full, 32, k, r0, p.e_batched ? b : 0, pol_stream);
-          }
-          __syncwarp();
-        }
-        named_bar_sync(12, LD_THREADS);
-        if (issuer) {
-          const int boff = p.ps_rows * b;
-          tma_gather4(stg + (2 + jb) * BLK + grp4 * 512, &tmPs, full, 32 * jb, idx[0] + boff, idx[1] + boff, idx[2] + boff,
-                      idx[3] + boff, pol_keep);
-        }
-      }
-    }
-  } else if (warp == W_MMA) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, 64);
-      mbar_wait(bar_w, 0);
-      const uint64_t desc_w1e = umma_desc(sbase + OFF_W1E);
-      const uint64_t desc_w1r = umma_desc(sbase + OFF_W1R);
-      const uint64_t desc_w2 = umma_desc(sbase + OFF_W2);
-      const uint64_t desc_rec = umma_desc(sbase + OFF_REC);
-      const uint64_t desc_st = umma_desc(sbase + OFF_ST);
-      int gr = 0, g1 = 0, g2 = 0;  // tiles with D_r issued; sub-tiles with GEMM1 / GEMM2 issued
-      uint32_t idle = 0;
-      while (g2 < n_sub) {
-        bool progress = false;
-        // D_r(T): receiver tile landed and every epilogue 1 of tile T-2 (which read D_r[T&1]) is done
-        if (gr < n_my && g2 >= (gr - 1) * d && mbar_test(bar_rec_full, (uint32_t)(gr & 1))) {
-          tc_fence_after();
-          const uint32_t dr = tmem_base + (gr & 1) * 64;
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_tf32(dr, desc_rec + (uint64_t)((jj * BLK) >> 4) + 2 * kk, desc_w1r + (uint64_t)((jj * WBLK) >> 4) + 2 * kk,
-                        idesc, (uint32_t)((jj | kk) != 0));
-          umma_commit(bar_dr_full + 8 * (gr & 1));
-          umma_commit(bar_rec_free);
-          ++gr;
-          progress = true;
-        }
-        if (g1 < n_sub && g1 <= g2 + 1) {
-          const int j = g1, ts = j & 1;
-          if (mbar_test(bar_full + 8 * ts, (uint32_t)((j >> 1) & 1)) &&
-              mbar_test(bar_d_free + 8 * ts, (uint32_t)(((j >> 1) & 1) ^ 1))) {
-            tc_fence_after();
-            const uint32_t dd = tmem_base + 128 + ts * 128;
-            const uint64_t a0 = desc_st + (uint64_t)((ts * 4 * BLK) >> 4);
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_tf32(dd, a0 + (uint64_t)((jj * BLK) >> 4) + 2 * kk, desc_w1e + (uint64_t)((jj * WBLK) >> 4) + 2 * kk,
-                          idesc, (uint32_t)((jj | kk) != 0));
-            umma_commit(bar_d1_full + 8 * ts);
-            E3_DBG(1, j);
-            ++g1;
-            progress = true;
-          }
-        }
-        if (g2 < g1) {
-          const int j = g2, ts = j & 1;
-          if (mbar_test(bar_hb_full + 8 * ts, (uint32_t)((j >> 1) & 1))) {
-            tc_fence_after();
-            const uint32_t dd = tmem_base + 128 + ts * 128;  // D2 overwrites D1
-            const uint32_t ht = dd + 64;
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_tf32_ts(dd, ht + (uint32_t)(jj * 32 + kk * 8), desc_w2 + (uint64_t)((jj * WBLK) >> 4) + 2 * kk, idesc,
-                             (uint32_t)((jj | kk) != 0));
-            umma_commit(bar_d2_full + 8 * ts);
-            E3_DBG(2, j);
-            ++g2;
-            progress = true;
-          }
-        }
-        if (progress) idle = 0;
-        else if (++idle > (1u << 26)) {
-          printf("nlam tc_ell: MMA issuer timeout (block %d gr %d g1 %d g2 %d)\n", blockIdx.x, gr, g1, g2);
-          __trap();
-        }
-      }
-    }
-  } else if (warp >= W_E1) {
-    // =============================== epilogue 1 (two groups alternate sub-tiles) ===============================
-    const int g1g = (warp - W_E1) >> 2;
-    const bool lead = ((warp - W_E1) & 3) == 0;
-    const int gbar = g1g ? 13 : 1;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    const uint32_t rsw = (uint32_t)(row * 128);
-    const int rx = row & 7;
-    for (int j = g1g; j < n_sub; j += 2) {
-      const int ts = j & 1;  // == g1g
-      const int ti = j / d;
-      if (lead) {
-        mbar_wait(bar_dr_full + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
-        mbar_wait(bar_full + 8 * ts, (uint32_t)((j >> 1) & 1));  // gathered P_s rows visible
-        mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((j >> 1) & 1));
-      }
-      named_bar_sync(gbar, E1_THREADS);
-      tc_fence_after();
-      if (lead && lane == 0) E3_DBG(3, j);
-      const uint8_t* ps = smem + OFF_ST + ts * 4 * BLK + 2 * BLK + rsw;
-      const uint32_t d1 = tmem_base + 128 + ts * 128 + t_lane;
-      const uint32_t dr = tmem_base + (ti & 1) * 64 + t_lane;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v[16], r[16];
-        tmem_ld16(d1 + c * 16, v);
-        tmem_ld16(dr + c * 16, r);
-        const uint8_t* psb = ps + (c >> 1) * BLK;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(psb + ((((c & 1) * 4 + k4) ^ rx) << 4));
-          v[4 * k4 + 0] = silu_fast(v[4 * k4 + 0] + r[4 * k4 + 0] + s4.x);  // P_s carries b1
-          v[4 * k4 + 1] = silu_fast(v[4 * k4 + 1] + r[4 * k4 + 1] + s4.y);
-          v[4 * k4 + 2] = silu_fast(v[4 * k4 + 2] + r[4 * k4 + 2] + s4.z);
-          v[4 * k4 + 3] = silu_fast(v[4 * k4 + 3] + r[4 * k4 + 3] + s4.w);
-        }
-        tmem_st16(d1 + 64 + c * 16, v);
-      }
-      tc_fence_before();
-      mbar_arrive(bar_hb_full + 8 * ts);  // hidden ready AND the shared-memory stage is free again
-      if (lead && lane == 0) E3_DBG(4, j);
-    }
-  } else {
-    // =============================== epilogue 2 (8 warps; accumulates the d sub-tiles in registers) ===============
-    const int q = warp & 3;
-    const int half = warp >> 2;
-    const int row = q * 32 + lane;
-    const int c0 = half * 32;
-    const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    const int pbar = 4 + q;
-    const uint32_t ln_col = tmem_base + 384 + t_lane;
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    int j = 0;
-    for (int ti = 0; ti < n_my; ++ti) {
-      const int w = blockIdx.x + ti * gridDim.x;
-      const int b = w / p.n_tiles, t = w - b * p.n_tiles;
-      for (int k = 0; k < d; ++k, ++j) {
-        const int ts = j & 1;
-        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((j >> 1) & 1));
-        if (tid == 0) E3_DBG(5, j);
-        named_bar_sync(2, G2_THREADS);
-        tc_fence_after();
-        if (tid == 0) E3_DBG(6, j);
-        float v[32];
-        tmem_ld32(tmem_base + 128 + ts * 128 + t_lane + c0, v);
-        tc_fence_before();
-        mbar_arrive(bar_d_free + 8 * ts);
-        float sm = 0.f, sq = 0.f;
-#pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const float4 bb = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k8);
-          v[4 * k8 + 0] += bb.x;
-          v[4 * k8 + 1] += bb.y;
-          v[4 * k8 + 2] += bb.z;
-          v[4 * k8 + 3] += bb.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          sm += v[i];
-          sq = fmaf(v[i], v[i], sq);
-        }
-        tmem_st2(ln_col + 2 * half, sm, sq);
-        tc_fence_before();
-        named_bar_sync(pbar, 64);
-        tc_fence_after();
-        float st4[4];
-        tmem_ld4(ln_col, st4);
-        const float mu = (st4[0] + st4[2]) * (1.0f / 64.0f);
-        const float ex2 = (st4[1] + st4[3]) * (1.0f / 64.0f);
-        const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
-#pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const float4 g4 = *reinterpret_cast<const float4*>(sprm + 128 + c0 + 4 * k8);
-          const float4 b4 = *reinterpret_cast<const float4*>(sprm + 192 + c0 + 4 * k8);
-          acc[4 * k8 + 0] += (v[4 * k8 + 0] - mu) * rstd * g4.x + b4.x;
-          acc[4 * k8 + 1] += (v[4 * k8 + 1] - mu) * rstd * g4.y + b4.y;
-          acc[4 * k8 + 2] += (v[4 * k8 + 2] - mu) * rstd * g4.z + b4.z;
-          acc[4 * k8 + 3] += (v[4 * k8 + 3] - mu) * rstd * g4.w + b4.w;
-        }
-        // the pair barrier also orders this sub-tile's scratch reads before the next sub-tile's writes
-        named_bar_sync(pbar, 64);
-        if (tid == 0) E3_DBG(7, j);
-      }
-      // aggregate of receiver r0+row: 128 contiguous bytes per thread (full lines, no partial sectors)
-      const long long r = (long long)t * 128 + row;
-      if (r < p.n_rec) {
-        const float sc = p.mean ? 1.0f / (float)d : 1.0f;
-        float4* o = reinterpret_cast<float4*>(p.aggr + ((long long)b * p.n_rec + r) * 64 + c0);
-#pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8)
-          o[k8] = make_float4(acc[4 * k8] * sc, acc[4 * k8 + 1] * sc, acc[4 * k8 + 2] * sc, acc[4 * k8 + 3] * sc);
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == W_MMA) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Sender-window variant: the 128*d edges of a receiver tile usually read far fewer than 128*d DISTINCT
 // senders (mesh->grid on MEPS: ~90 mesh nodes serve the 512 edges of a tile).  The graph handle lists
 // the distinct senders of every tile (<= 128, else this variant is not used) and the window row of every
@@ -921,7 +574,7 @@ bool tc_ell_supported(const NlamGraph* g, const NlamMlp* edge_mlp, int flags, co
   static int on = -1;
   if (on < 0) on = getenv("NLAM_TC_NO_ELL") ? 0 : 1;
   if (!on || has_edge_out) return false;
-  if (!g || g->uniform_degree < 1 || g->uniform_degree > 8) return false;
+  if (!g || g->uniform_degree < 1 || g->uniform_degree > 8 || !g->ell_window) return false;  // <= 128 distinct senders per tile
   if (!tc_edge_supported(g, edge_mlp, flags)) return false;
   return aligned16(send) && aligned16(rec) && send_bs % 4 == 0 && rec_bs % 4 == 0;
 }
@@ -983,19 +636,12 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   p.n_rec = nr;
   p.B = B;
   p.n_tiles = (int)((nr + 127) / 128);
-  static unsigned attr_mask = 0;
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
-  if (!(attr_mask & (1u << (dev & 31)))) {
-    NLAM_CUDA_OK(cudaFuncSetAttribute(tc_ell_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3::SMEM));
-    attr_mask |= 1u << (dev & 31);
-  }
   const long long n_work = (long long)p.n_tiles * p.B;
   NLAM_REQUIRE(n_work * d < (1LL << 31) - 4096, NLAM_E_UNSUPPORTED, "tc_ell_edge: too many work items");
   const int grid = (int)std::min<long long>(n_work, num_sms());
-  static int use_window = -1;
-  if (use_window < 0) use_window = getenv("NLAM_TC_ELL_NO_WINDOW") ? 0 : 1;
-  const bool window = use_window && g->ell_window;
+  NLAM_REQUIRE(g->ell_window, NLAM_E_UNSUPPORTED, "tc_ell_edge: a receiver tile reads more than 128 distinct senders");
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("NLAM_TC_TIMELINE") ? 1 : 0;
@@ -1004,7 +650,7 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     NLAM_CUDA_OK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-  if (window) {
+  {
     static unsigned attr_mask_w = 0;
     if (!(attr_mask_w & (1u << (dev & 31)))) {
       NLAM_CUDA_OK(cudaFuncSetAttribute(tc_ell_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e4::SMEM));
@@ -1035,9 +681,6 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     q.prefetch = pf;
     ProfScope ps("tc_ell_window_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, false, 64));
     tc_ell_window_kernel<<<grid, e4::THREADS, e4::SMEM, st>>>(me, mrec, mw1, mw2, mps, mo, q);
-  } else {
-    ProfScope ps("tc_ell_edge_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, false, 64));
-    tc_ell_edge_kernel<<<grid, e3::THREADS, e3::SMEM, st>>>(me, mrec, mw1, mw2, mps, p);
   }
   count_launch();
   if (dbg_on) {

@@ -510,12 +510,6 @@ tc_edge3_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
 int edge_projections(const float* send, int64_t send_bs, int64_t ns, int Bs, const float* rec, int64_t rec_bs, int64_t nr,
                      int Br, const float* w1, const float* b1, float* Ps, float* Pr, cudaStream_t st);  // tc2.cu
 
-bool tc_edge3_enabled() {
-  static int on = -1;
-  if (on < 0) on = getenv("NLAM_TC_NO_EDGE3") ? 0 : 1;
-  return on != 0;
-}
-
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t st, float* ws) {

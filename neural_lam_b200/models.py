@@ -79,6 +79,15 @@ class StepPredictor(nn.Module):
                             datastore.state_mean, datastore.state_std)
         for name in clamping.BUFFER_NAMES:
             self.register_buffer(name, getattr(clamp, name))
+        # per-variable form for the fused kernel (nlam_step_epilogue_clamped): kind 0 none / 1 sigmoid / 2 lower / 3 upper
+        d = self.num_state_vars
+        kind, lo, up = torch.zeros(d, dtype=torch.int32), torch.zeros(d), torch.zeros(d)
+        kind[clamp.clamp_lower_upper_idx], lo[clamp.clamp_lower_upper_idx], up[clamp.clamp_lower_upper_idx] = (
+            1, clamp.sigmoid_lower_lims, clamp.sigmoid_upper_lims)
+        kind[clamp.clamp_lower_idx], lo[clamp.clamp_lower_idx] = 2, clamp.softplus_lower_lims
+        kind[clamp.clamp_upper_idx], up[clamp.clamp_upper_idx] = 3, clamp.softplus_upper_lims
+        for name, t in (("_clamp_kind", kind), ("_clamp_lo", lo), ("_clamp_up", up)):
+            self.register_buffer(name, t, persistent=False)
 
     @property
     def predicts_std(self):
@@ -221,9 +230,11 @@ class BaseGraphModel(StepPredictor):
             pred_std = torch.nn.functional.softplus(pred_std_raw)
         else:
             pred_delta_mean, pred_std = net_output, None
-        if not torch.is_grad_enabled() and not self.output_std and not self.clamps_output:
-            # rescale (base.py:339) + residual (base.py:342) in one kernel
-            return ops.step_epilogue(pred_delta_mean, prev_state, None, None, self.diff_std, self.diff_mean), None
+        if not torch.is_grad_enabled():
+            # rescale (base.py:339) + (clamped) residual update (base.py:342, step_predictors/base.py:366-396) in one kernel
+            clamp = (self._clamp_kind, self._clamp_lo, self._clamp_up) if self.clamps_output else None
+            return ops.step_epilogue(pred_delta_mean.contiguous(), prev_state, None, None, self.diff_std, self.diff_mean,
+                                     clamp=clamp), pred_std
         rescaled = pred_delta_mean * self.diff_std + self.diff_mean
         return self.get_clamped_new_state(rescaled, prev_state), pred_std
 
@@ -232,10 +243,6 @@ class BaseGraphModel(StepPredictor):
         """Inference step with the ARForecaster boundary mix (autoregressive.py:128-131) fused
         into the step epilogue kernel.  ``out``: optional preallocated (B,G,d) tensor for the new state."""
         assert not self.output_std
-        if self.clamps_output:  # clamped update (elementwise torch ops), then the boundary mix
-            pred, _ = self.forward(prev_state, prev_prev_state, forcing)
-            new_state = boundary_mask * boundary_state + (1.0 - boundary_mask) * pred
-            return new_state if out is None else out.copy_(new_state)
         B = prev_state.shape[0]
         grid_emb = self.grid_embedder.apply_rows(
             [prev_state, prev_prev_state, forcing, self.expand_to_batch(self.grid_static_features, B)])
@@ -244,13 +251,16 @@ class BaseGraphModel(StepPredictor):
         grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)
         mesh_rep = self.process_step(mesh_rep, st)
         grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
-        fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, boundary_state, boundary_mask, self.diff_std,
-                                self.diff_mean, flags=self.output_map.nlam_flags, out=out)
-        if fused is not None:
-            return fused
+        clamp = (self._clamp_kind, self._clamp_lo, self._clamp_up) if self.clamps_output else None
+        if clamp is None:
+            fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, boundary_state, boundary_mask, self.diff_std,
+                                    self.diff_mean, flags=self.output_map.nlam_flags, out=out)
+            if fused is not None:
+                return fused
         net_output = self.output_map(grid_rep)
+        # rescale + (clamped) update + boundary mix in one kernel
         return ops.step_epilogue(net_output, prev_state, boundary_state, boundary_mask, self.diff_std, self.diff_mean,
-                                 out=out)
+                                 out=out, clamp=clamp)
 
 
 class GraphLAM(BaseGraphModel):

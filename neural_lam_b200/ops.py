@@ -335,8 +335,10 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     return rec_out, edge_out, aggr
 
 
-def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None):
-    """new = bmask*boundary + (1-bmask)*(prev + net_out*diff_std + diff_mean) (no-grad path)."""
+def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None, clamp=None):
+    """new = bmask*boundary + (1-bmask)*(prev + net_out*diff_std + diff_mean) (no-grad path); ``clamp`` =
+    (kind int32 (D), lo (D), up (D)): the clamped update of models/step_predictors/base.py:366-396 instead of the plain
+    residual for the variables with limits."""
     L = _lib.lib()
     net_out, prev = net_out.contiguous(), prev.contiguous()
     _require_cuda(net_out, prev, diff_std, diff_mean, boundary, bmask)
@@ -351,11 +353,17 @@ def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None)
         boundary, bmask = boundary.contiguous(), bmask.contiguous()
         assert bmask.numel() == G
     with torch.cuda.device(net_out.device):
-        _lib.check(L.nlam_step_epilogue(net_out.data_ptr(), prev.data_ptr(),
-                                        boundary.data_ptr() if boundary is not None else None,
-                                        bmask.data_ptr() if boundary is not None else None,
-                                        diff_std.data_ptr(), diff_mean.data_ptr(), out.data_ptr(), B, G, D,
-                                        _stream_ptr(net_out.device)))
+        bp = boundary.data_ptr() if boundary is not None else None
+        mp = bmask.data_ptr() if boundary is not None else None
+        if clamp is not None:
+            kind, lo, up = clamp
+            assert kind.dtype == torch.int32 and kind.numel() == D and lo.numel() == D and up.numel() == D
+            _lib.check(L.nlam_step_epilogue_clamped(net_out.data_ptr(), prev.data_ptr(), bp, mp, diff_std.data_ptr(),
+                                                    diff_mean.data_ptr(), kind.data_ptr(), lo.data_ptr(), up.data_ptr(),
+                                                    out.data_ptr(), B, G, D, _stream_ptr(net_out.device)))
+        else:
+            _lib.check(L.nlam_step_epilogue(net_out.data_ptr(), prev.data_ptr(), bp, mp, diff_std.data_ptr(),
+                                            diff_mean.data_ptr(), out.data_ptr(), B, G, D, _stream_ptr(net_out.device)))
     return out
 
 

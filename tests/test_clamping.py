@@ -86,3 +86,41 @@ def test_clamp_configuration_errors_and_inactive():
     assert not none.active
     x, d = torch.randn(1, 4, 6), torch.randn(1, 4, 6)
     torch.testing.assert_close(none(d, x), x + d, rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_boundary", [False, True])
+def test_fused_clamped_step_epilogue_kernel(with_boundary):
+    """nlam_step_epilogue_clamped (rescale + clamped update + boundary mix in one launch) vs the oracle restatement of
+    get_clamped_new_state + the boundary mix of autoregressive.py:128-131; fp32 elementwise: 5e-6."""
+    from neural_lam_b200 import models, ops, synthetic
+
+    spec = synthetic.make_graph_spec(16, 16, hierarchical=False, n_levels=1)
+    ds = synthetic.SyntheticDatastore(spec, d_state=6, d_forcing=6, d_static=1, boundary_width=1)
+    ds.state_var_names = NAMES
+    ds.state_mean, ds.state_std = _stats(torch.float32)
+    model = models.GraphLAM(ds, spec, hidden_dim=16, processor_layers=1, output_clamping_lower=LOWER,
+                            output_clamping_upper=UPPER).cuda()
+    assert model.clamps_output and model._clamp_kind.tolist() == [1, 2, 3, 0, 1, 0]
+    g = torch.Generator().manual_seed(0)
+    B, G, D = 3, 256, 6
+    prev = torch.randn(B, G, D, generator=g)
+    for i, n in enumerate(NAMES):  # clamped variables start inside their limits
+        lo = (LOWER[n] - ds.state_mean[i]) / ds.state_std[i] if n in LOWER else None
+        up = (UPPER[n] - ds.state_mean[i]) / ds.state_std[i] if n in UPPER else None
+        if lo is not None and up is not None:
+            prev[:, :, i] = lo + (up - lo) * torch.rand(B, G, generator=g)
+        elif lo is not None:
+            prev[:, :, i] = lo + torch.rand(B, G, generator=g) * 3
+        elif up is not None:
+            prev[:, :, i] = up - torch.rand(B, G, generator=g) * 3
+    net_out = torch.randn(B, G, D, generator=g) * 2
+    std, mean = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
+    bnd, mask = torch.randn(B, G, D, generator=g), (torch.rand(G, 1, generator=g) < 0.3).float()
+    want = rp.clamped_new_state(net_out * std + mean, prev, NAMES, LOWER, UPPER, ds.state_mean, ds.state_std)
+    if with_boundary:
+        want = mask * bnd + (1 - mask) * want
+    got = ops.step_epilogue(net_out.cuda(), prev.cuda(), bnd.cuda() if with_boundary else None,
+                            mask.cuda() if with_boundary else None, std.cuda(), mean.cuda(),
+                            clamp=(model._clamp_kind, model._clamp_lo, model._clamp_up))
+    torch.testing.assert_close(got.cpu(), want, rtol=5e-6, atol=5e-6)

@@ -300,9 +300,9 @@ def test_model_rollout_tf32_vs_oracle(kind):
 
 
 def test_split_edge_kernel_v2_matches_v1_and_oracle():
-    """The split-first-Linear edge kernels (tc5.cu and its predecessor tc2.cu; forced with NLAM_TC_EDGE=v2
-    [+ NLAM_TC_NO_EDGE3=1] in a fresh process, the selection is read once per process) against the fp64
-    oracle and the K=192 kernel."""
+    """Both formulations of the first edge Linear — split (node projections + tc5.cu, NLAM_TC_EDGE=v2) and K=192 with
+    raw gathered rows (tc.cu, NLAM_TC_EDGE=v1); forced in a fresh process, the selection is read once per process —
+    against the fp64 oracle."""
     import os
     import subprocess
     import sys
@@ -335,16 +335,14 @@ for upd, aggr in ((True, "sum"), (False, "mean")):
 print("LAUNCHES", nlb._lib.lib().nlam_launch_count())
 '''
     outs = {}
-    for mode, extra in (("v1", {}), ("v2", {}), ("v2", {"NLAM_TC_NO_EDGE3": "1"})):
+    for mode, extra in (("v1", {}), ("v2", {})):
         env = dict(os.environ, NLAM_TC_EDGE=mode, **extra)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         outs[mode + ("_tc2" if extra else "")] = int([l for l in r.stdout.splitlines() if l.startswith("LAUNCHES")][0].split()[1])
-    # the split formulations (tc5.cu by default, tc2.cu with NLAM_TC_NO_EDGE3=1) issue one extra launch per
-    # InteractionNet call: both node projections in a single grid
+    # the split formulation issues one extra launch per InteractionNet call: both node projections in a single grid
     assert outs["v2"] == outs["v1"] + 2
-    assert outs["v2_tc2"] == outs["v2"]
 
 
 def _ell_graph(ns, nr, d, seed):
