@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — forecast-steps/sec of the GraphLAM hot path on B200 (contract in the task brief).
 
-Workload (BASELINE.json configs[1]): MEPS-shaped 268x238 grid (xy shape (238,268)), multiscale
+Workload (BASELINE.json configs[1]): MEPS-shaped 268x238 grid (xy shape (268, 238), as the reference's create_graph takes it), multiscale
 mesh (6 561 nodes, 57 616 m2m / 100 656 g2m / 255 136 m2g edges), GraphLAM hidden_dim=64,
 4 processor layers, fp32 I/O, synthetic inputs (seeded), random-init weights (seed 42).
 
@@ -45,9 +45,9 @@ D_STATE, D_FORCING, D_STATIC = 17, 18, 4
 # BASELINE.json configs (1-based as listed there).  Config 2 is the one the metric is quoted on (default); 3 and 4 are
 # the H = 128 / 256 workloads (generic tcgen05 path, tc7.cu), 4 as its single-GPU form (B = 1).
 CONFIGS = {
-    2: dict(grid=(238, 268), hierarchical=False, n_levels=None, model="graph_lam", hidden=64, layers=4, batch=32,
+    2: dict(grid=(268, 238), hierarchical=False, n_levels=None, model="graph_lam", hidden=64, layers=4, batch=32,
             workload="MEPS 268x238 grid, multiscale mesh, GraphLAM hidden_dim=64, 4 processor layers (BASELINE.json configs[1])"),
-    3: dict(grid=(238, 268), hierarchical=True, n_levels=3, model="hi_lam", hidden=128, layers=6, batch=8,
+    3: dict(grid=(268, 238), hierarchical=True, n_levels=3, model="hi_lam", hidden=128, layers=6, batch=8,
             workload="MEPS 268x238 grid, 3-level hierarchical mesh, HiLAM hidden_dim=128, 6 processor layers "
                      "(BASELINE.json configs[2])"),
     4: dict(grid=(1024, 1024), hierarchical=False, n_levels=None, model="graph_lam", hidden=256, layers=4, batch=1,
@@ -749,11 +749,11 @@ def main():
     global CFG, METRIC
     CFG = CONFIGS[args.config]
     METRIC = ("forecast-steps/sec (268x238 grid, hidden=64)" if args.config == 2 else
-              f"forecast-steps/sec ({CFG['grid'][1]}x{CFG['grid'][0]} grid, hidden={CFG['hidden']}, BASELINE config {args.config})")
+              f"forecast-steps/sec ({CFG['grid'][0]}x{CFG['grid'][1]} grid, hidden={CFG['hidden']}, BASELINE config {args.config})")
     if args.parallelism == "partition" and args.config == 2 and "--config" not in sys.argv:
         args.config = 4
         CFG = CONFIGS[4]
-        METRIC = f"forecast-steps/sec ({CFG['grid'][1]}x{CFG['grid'][0]} grid, hidden={CFG['hidden']}, BASELINE config 4)"
+        METRIC = f"forecast-steps/sec ({CFG['grid'][0]}x{CFG['grid'][1]} grid, hidden={CFG['hidden']}, BASELINE config 4)"
     if not args.batch:
         args.batch = CFG["batch"]
     if args.config == 4:  # the fp64 / fp32 CPU oracle takes minutes per step at 1 M grid nodes

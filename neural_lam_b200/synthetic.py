@@ -13,7 +13,7 @@ generator that follows the same topology rules on a regular grid:
     3x3 block (:596-611); hierarchical: levels stay separate, up edges = 1-nearest coarser node
     (:485-509), down edges = reversed with negated offsets (:562-569);
   * g2m: grid nodes within ``0.67*dm`` of a bottom mesh node, ``dm`` = mesh spacing along the
-    2nd axis (:698-758); m2g: 4 nearest bottom mesh nodes of every grid node (:779-792);
+    1st axis (:698-758); m2g: 4 nearest bottom mesh nodes of every grid node (:779-792);
   * node order: mesh node (i,j) -> i*n+j, grid node (i,j) -> i*Ny+j (sorted labels, :667-676).
 
 ``normalize_graph`` applies what ``load_graph`` does at load time (reference
@@ -141,7 +141,9 @@ def make_graph_spec(Nx, Ny, hierarchical=False, n_levels=None, spacing=1.0):
     # grid <-> bottom mesh
     bottom = pos[0]
     n0 = ns[0]
-    dm = np.sqrt(((bottom[1] - bottom[0]) ** 2).sum())  # nodes (0,1) and (0,0): spacing along 2nd axis
+    # mesh nodes (1, 0) and (0, 0): the spacing along the FIRST axis (create_graph.py:702-704 indexes the node labels
+    # (0, 1, 0) and (0, 0, 0) = (level prefix, i, j))
+    dm = np.sqrt(((bottom[n0] - bottom[0]) ** 2).sum())
     gtree = cKDTree(grid_xy)
     neigh = gtree.query_ball_point(bottom, dm * 0.67)
     counts = np.fromiter((len(x) for x in neigh), dtype=np.int64, count=len(neigh))

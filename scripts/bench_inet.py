@@ -13,9 +13,9 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "m2m"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 dev = torch.device("cuda:0")
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 torch.manual_seed(0)
-G, M = 238 * 268, 6561
+G, M = 268 * 238, 6561
 if kind == "g2m":
     ei = spec["g2m_edge_index"]
     net = nlb.InteractionNet(ei, 64, update_edges=False).to(dev)

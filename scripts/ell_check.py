@@ -48,9 +48,9 @@ check("d=5 multi-tile per CTA", 2000, 128 * 150 + 17, 5, 2)
 check("d=4 window multi-tile per CTA", 120, 128 * 150 + 17, 4, 2)
 check("d=1 window multi-tile", 5000, 128 * 300 + 5, 1, 3, aggr="mean")
 
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ei = spec["m2g_edge_index"]
-G = 238 * 268
+G = 268 * 238
 for B in (1, 8, 32):
     net = nlb.InteractionNet(ei, 64, update_edges=False, math="tf32").to(dev)
     mesh = torch.randn(B, 6561, 64, device=dev)

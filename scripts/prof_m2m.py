@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 math = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 dev = torch.device("cuda:0")
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ei = spec["m2m_edge_index"]
 torch.manual_seed(0)
 net = nlb.InteractionNet(ei, 64, math=math).to(dev)

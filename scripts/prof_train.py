@@ -5,7 +5,7 @@ import torch
 from neural_lam_b200 import models, ops, synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda:0")
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ds = synthetic.SyntheticDatastore(spec, d_state=17, d_forcing=18, d_static=4, boundary_width=10)
 torch.manual_seed(42)
 m = models.GraphLAM(ds, spec, hidden_dim=64, processor_layers=4).to(dev)

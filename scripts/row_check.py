@@ -49,7 +49,7 @@ check("K=128 many tiles per CTA", [128, 64, 64], [(3, 128 * 400 + 3, 64), (3, 12
 check("K=64 many tiles per CTA", [64, 64, 64], [(2, 128 * 700 + 77, 64)], 0)
 check("one row", [64, 64, 64], [(1, 1, 64)], 0)
 
-G = 238 * 268
+G = 268 * 238
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for B in (8, 32):
     for name, bp, ns, res in (("encoding K=64 res", [64, 64, 64], 1, 0), ("node K=128 res", [128, 64, 64], 2, 0)):

@@ -85,7 +85,7 @@ check_edge("edge many empty receivers", 40, 600, 300, 2, True)
 
 print("== MEPS m2m timing ==", flush=True)
 from neural_lam_b200 import synthetic
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ei = spec["m2m_edge_index"]
 for B in (1, 4, 8):
     for math in ("tf32", "fp32"):

@@ -6,7 +6,7 @@ import neural_lam_b200 as nlb
 from neural_lam_b200 import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ei = spec["m2m_edge_index"]
 torch.manual_seed(0)
 net = nlb.InteractionNet(ei, 64, math="tf32").to(dev)

@@ -6,12 +6,12 @@ import neural_lam_b200 as nlb
 from neural_lam_b200 import synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
-spec = synthetic.make_graph_spec(238, 268)
+spec = synthetic.make_graph_spec(268, 238)
 ei = spec["m2g_edge_index"]
 torch.manual_seed(0)
 net = nlb.InteractionNet(ei, 64, update_edges=False, math="tf32").to(dev)
 mesh = torch.randn(B, 6561, 64, device=dev)
-grid = torch.randn(B, 238 * 268, 64, device=dev)
+grid = torch.randn(B, 268 * 238, 64, device=dev)
 edge = torch.randn(1, ei.shape[1], 64, device=dev).expand(B, -1, -1)
 with torch.no_grad():
     for i in range(3):

@@ -7,7 +7,7 @@ from neural_lam_b200 import ops, _lib
 B = 8
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dev = torch.device("cuda:0")
-G = 238 * 268
+G = 268 * 238
 m = nlb.make_mlp([64 * ns, 64, 64], layer_norm=True).to(dev)
 ds = [torch.randn(B, G, 64, device=dev) for _ in range(ns)]
 with torch.no_grad():

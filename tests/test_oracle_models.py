@@ -102,3 +102,64 @@ def test_legacy_graph_directory_is_zero_indexed(tmp_path):
     (tmp_path / "metainfo.yaml").write_text("spec_version: 9.9\n")
     with pytest.raises(ValueError):
         synthetic.load_graph(str(tmp_path), spec["grid_xy"])
+
+
+def _edge_set(ei, feat):
+    return sorted((int(a), int(b)) + tuple(round(float(x), 4) for x in f) for a, b, f in zip(ei[0], ei[1], feat))
+
+
+@pytest.mark.skipif(not load_reference.available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("hier", [False, True])
+def test_graph_generator_matches_reference_create_graph(hier):
+    """``synthetic.make_graph_spec`` (vectorised) against the reference's own ``create_graph`` (networkx loops,
+    create_graph.py:356-862, run unmodified through oracle/load_create_graph.py) on a NON-square grid: identical edge
+    sets and edge features for g2m (radius 0.67 x the mesh spacing along the first axis), m2g (4 nearest), every m2m
+    level, the up / down edges, and identical mesh node positions."""
+    from neural_lam_b200 import synthetic
+    from oracle import load_create_graph as lcg
+
+    if not lcg.available():
+        pytest.skip("networkx / reference create_graph not available")
+    ref = lcg.reference_create_graph(30, 27, hierarchical=hier)
+    mine = synthetic.make_graph_spec(30, 27, hierarchical=hier)
+    for k in ("g2m", "m2g"):
+        assert _edge_set(ref[f"{k}_edge_index"], ref[f"{k}_features"]) == _edge_set(mine[f"{k}_edge_index"], mine[f"{k}_features"]), k
+    m_ei = mine["m2m_edge_index"] if hier else [mine["m2m_edge_index"]]
+    m_f = mine["m2m_features"] if hier else [mine["m2m_features"]]
+    mesh = mine["mesh_static_features"] if hier else [mine["mesh_static_features"]]
+    assert len(ref["m2m_edge_index"]) == len(m_ei)
+    for l in range(len(m_ei)):
+        assert _edge_set(ref["m2m_edge_index"][l], ref["m2m_features"][l]) == _edge_set(m_ei[l], m_f[l]), f"m2m level {l}"
+        torch.testing.assert_close(ref["mesh_features"][l].float(), mesh[l], rtol=1e-6, atol=1e-5)
+    if hier:
+        for k in ("mesh_up", "mesh_down"):
+            for l in range(len(mine[f"{k}_edge_index"])):
+                assert _edge_set(ref[f"{k}_edge_index"][l], ref[f"{k}_features"][l]) == \
+                    _edge_set(mine[f"{k}_edge_index"][l], mine[f"{k}_features"][l]), f"{k} level {l}"
+
+
+@pytest.mark.skipif(not load_reference.available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("hier", [False, True])
+def test_saved_graphs_pass_the_reference_validator(hier, tmp_path):
+    """``synthetic.save_graph`` output through the reference's stand-alone on-disk validator docs/validate_graph.py."""
+    import importlib.util
+    import sys
+
+    from neural_lam_b200 import synthetic
+
+    path = os.path.join(load_reference.REFERENCE_ROOT, "docs", "validate_graph.py")
+    spec = importlib.util.spec_from_file_location("_ref_validate_graph", path)
+    vg = importlib.util.module_from_spec(spec)
+    sys.modules["_ref_validate_graph"] = vg
+    spec.loader.exec_module(vg)
+    g = synthetic.make_graph_spec(30, 27, hierarchical=hier)
+    synthetic.save_graph(g, str(tmp_path))
+    synthetic.save_graph_csr_cache(str(tmp_path))     # the extra <set>_csr.pt files must not disturb the validator
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        report, _, props = vg.validate_graph_directory(str(tmp_path))
+    assert report.ok, [r for r in report.results if getattr(r, "status", "PASS") != "PASS"]
+    assert props.is_hierarchical == hier and props.num_grid_nodes == 810
+    assert props.num_mesh_nodes_per_level == ([81, 9] if hier else [81])

@@ -1,6 +1,6 @@
 """Parity at the REAL sizes of the BASELINE configs (`-m gpu`).
 
-  * config 2: MEPS 238x268 grid (63 784 grid nodes, 6 561 mesh nodes, in-degree up to 32, 57 616 / 100 656 /
+  * config 2: MEPS 268x238 grid (63 784 grid nodes, 6 561 mesh nodes, in-degree up to 32, 57 616 / 100 656 /
     255 136 edges), multiscale GraphLAM H=64, P=4, B=2: 1 step and a 19-step rollout (config 5's rollout length);
   * config 3's graph: the same grid with a THREE-level hierarchical mesh (6 561 / 729 / 81 nodes), HiLAM H=64;
   * config 1 through ``math="auto"``.
@@ -57,12 +57,12 @@ def _check(name, got, want64, ref_tf32):
 
 @pytest.mark.gpu
 def test_config2_real_size_19_step_rollout():
-    spec = synthetic.make_graph_spec(238, 268, hierarchical=False)
+    spec = synthetic.make_graph_spec(268, 238, hierarchical=False)
     ds = synthetic.SyntheticDatastore(spec, d_state=17, d_forcing=18, d_static=4, boundary_width=10)
     assert ds.num_grid_nodes == 63784 and spec["m2m_edge_index"].shape[1] == 57616
     assert spec["g2m_edge_index"].shape[1] == 100656 and spec["m2g_edge_index"].shape[1] == 255136
     got, want64, ref_tf32, fc, (init, forc, bnd) = _rollouts(models.GraphLAM, "graph_lam", spec, ds, B=2, T=19, P=4)
-    _check("config 2 (MEPS 238x268, GraphLAM H=64 P=4, B=2, 19 AR steps)", got, want64, ref_tf32)
+    _check("config 2 (MEPS 268x238, GraphLAM H=64 P=4, B=2, 19 AR steps)", got, want64, ref_tf32)
     # eager forward (reference-shaped call path) and the host-buffer API agree with the graph replay
     with torch.no_grad():
         eager, _ = fc(init[:, :, :, :].cuda(), forc[:, :2].cuda(), bnd[:, :2].cuda())
@@ -73,11 +73,11 @@ def test_config2_real_size_19_step_rollout():
 
 @pytest.mark.gpu
 def test_config3_graph_three_level_hilam_real_size():
-    spec = synthetic.make_graph_spec(238, 268, hierarchical=True, n_levels=3)
+    spec = synthetic.make_graph_spec(268, 238, hierarchical=True, n_levels=3)
     assert [m.shape[0] for m in spec["mesh_static_features"]] == [6561, 729, 81]
     ds = synthetic.SyntheticDatastore(spec, d_state=17, d_forcing=18, d_static=4, boundary_width=10)
     got, want64, ref_tf32, _, _ = _rollouts(models.HiLAM, "hi_lam", spec, ds, B=1, T=2, P=2)
-    _check("config 3 graph (MEPS 238x268, 3-level HiLAM H=64 P=2, B=1, 2 AR steps)", got, want64, ref_tf32)
+    _check("config 3 graph (MEPS 268x238, 3-level HiLAM H=64 P=2, B=1, 2 AR steps)", got, want64, ref_tf32)
 
 
 @pytest.mark.gpu
