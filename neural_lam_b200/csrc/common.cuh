@@ -173,6 +173,8 @@ struct NlamGraph {
   // senders ell_u[128*t ..] (ascending, padded to a multiple of 4); CSR edge k reads window row ell_loc[k].
   // ell_window == 0 if some tile reads more than 128 distinct senders (or the degree is not uniform).
   int32_t ell_window = 0;
+  int32_t ell_nt = 0;           // number of ELL receiver tiles
+  int32_t* ell_r0 = nullptr;    // ell_nt + 1: first receiver of every ELL tile (tile t = receivers [ell_r0[t], ell_r0[t+1]), <= 128)
   int32_t* ell_u = nullptr;
   int32_t* ell_nu = nullptr;
   uint8_t* ell_loc = nullptr;

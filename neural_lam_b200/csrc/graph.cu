@@ -227,37 +227,39 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
       win_nu[t] = (int32_t)nu;
     }
   }
-  // sender windows of the ELL kernel (tc3.cu)
-  std::vector<int32_t> ell_u, ell_nu;
+  // Receiver tiles + sender windows of the ELL kernel (tc3.cu): a tile is up to 128 CONSECUTIVE receivers whose d*nrec
+  // edges read at most 128 distinct senders (the window); a tile is cut short where the next receivers would overflow the
+  // window (mesh->grid on a 268 x 238 grid: a 128-receiver block that wraps around a grid row reads up to 135 mesh nodes),
+  // so every uniform-degree edge set has a tiling.
+  std::vector<int32_t> ell_u, ell_nu, ell_r0;
   std::vector<uint8_t> ell_loc;
   if (g->uniform_degree >= 1 && g->uniform_degree <= 8) {
-    const int64_t d = g->uniform_degree, nt = (n_rec + 127) / 128;
-    ell_u.assign((size_t)nt * 128, 0);
-    ell_nu.assign((size_t)nt, 0);
+    const int64_t d = g->uniform_degree;
     ell_loc.assign((size_t)E, 0);
-    bool ok = true;
     std::vector<int32_t> u;
-    for (int64_t t = 0; t < nt && ok; ++t) {
-      const int64_t k0 = d * 128 * t, k1 = std::min<int64_t>(E, d * 128 * (t + 1));
-      u.assign(src.begin() + k0, src.begin() + k1);
-      std::sort(u.begin(), u.end());
-      u.erase(std::unique(u.begin(), u.end()), u.end());
-      if (u.size() > 128) {
-        ok = false;
-        break;
+    int64_t r0 = 0;
+    while (r0 < n_rec) {
+      int64_t nrec = std::min<int64_t>(128, n_rec - r0);
+      for (;;) {
+        u.assign(src.begin() + d * r0, src.begin() + d * (r0 + nrec));
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        if (u.size() <= 128) break;
+        nrec -= (nrec > 16) ? 8 : 1;  // 8 receivers of degree <= 8 always fit
       }
-      for (int64_t k = k0; k < k1; ++k)
+      for (int64_t k = d * r0; k < d * (r0 + nrec); ++k)
         ell_loc[k] = (uint8_t)(std::lower_bound(u.begin(), u.end(), src[k]) - u.begin());
       const size_t nu = (u.size() + 3) / 4 * 4;
-      for (size_t i = 0; i < nu; ++i) ell_u[(size_t)t * 128 + i] = u[std::min(i, u.size() - 1)];
-      ell_nu[t] = (int32_t)nu;
+      const size_t base = ell_u.size();
+      ell_u.resize(base + 128, 0);
+      for (size_t i = 0; i < nu; ++i) ell_u[base + i] = u[std::min(i, u.size() - 1)];
+      ell_nu.push_back((int32_t)nu);
+      ell_r0.push_back((int32_t)r0);
+      r0 += nrec;
     }
-    g->ell_window = ok ? 1 : 0;
-    if (!ok) {
-      ell_u.clear();
-      ell_nu.clear();
-      ell_loc.clear();
-    }
+    ell_r0.push_back((int32_t)n_rec);
+    g->ell_window = 1;
+    g->ell_nt = (int32_t)ell_nu.size();
   }
   g->h_tile_rec = tile_rec;
   g->h_rowptr = rowptr;
@@ -281,7 +283,7 @@ extern "C" int nlam_graph_create(NlamGraph** out, const int64_t* edge_index, int
       (rc = upload(&g->sptr, sptr)) || (rc = upload(&g->sperm, sperm)) ||
       (rc = upload(&g->tile_rec, tile_rec)) || (rc = upload(&g->tile_e0, tile_e0)) ||
       (rc = upload(&g->tile_meta, tile_meta)) || (rc = upload(&g->ell_u, ell_u)) ||
-      (rc = upload(&g->ell_nu, ell_nu)) || (rc = upload(&g->ell_loc, ell_loc)) ||
+      (rc = upload(&g->ell_nu, ell_nu)) || (rc = upload(&g->ell_loc, ell_loc)) || (rc = upload(&g->ell_r0, ell_r0)) ||
       (rc = upload(&g->win_u, win_u)) || (rc = upload(&g->win_nu, win_nu)) || (rc = upload(&g->win_loc, win_loc))) {
     cudaSetDevice(prev_dev);
     nlam_graph_destroy(g);
@@ -310,6 +312,7 @@ extern "C" void nlam_graph_destroy(NlamGraph* g) {
   cudaFree(g->ell_u);
   cudaFree(g->ell_nu);
   cudaFree(g->ell_loc);
+  cudaFree(g->ell_r0);
   cudaFree(g->win_u);
   cudaFree(g->win_nu);
   cudaFree(g->win_loc);

@@ -106,6 +106,7 @@ struct EllWinParams {
   long long n_rec;
   int B;
   int n_tiles;
+  const int32_t* r0;     // n_tiles + 1: first receiver of every tile (variable tiles of <= 128 receivers)
   int prefetch;
   long long* dbg;
 };
@@ -217,17 +218,18 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         const int w = blockIdx.x + ti * gridDim.x;
         int b, t;
         work_bt(w, b, t);
-        const int r0 = t * 128;
+        const int r0 = __ldg(p.r0 + t);
         if (p.prefetch && ti + 1 < n_my) {
           // pull the next tile's operands into L2 while this one is processed
           const int wn = w + gridDim.x;
           int bn, tn;
           work_bt(wn, bn, tn);
-          tma_prefetch_3d(&tmRec, 0, tn * 128, p.rec_batched ? bn : 0);
-          tma_prefetch_3d(&tmRec, 32, tn * 128, p.rec_batched ? bn : 0);
+          const int rn = __ldg(p.r0 + tn);
+          tma_prefetch_3d(&tmRec, 0, rn, p.rec_batched ? bn : 0);
+          tma_prefetch_3d(&tmRec, 32, rn, p.rec_batched ? bn : 0);
           for (int k = 0; k < d; ++k) {
-            tma_prefetch_4d(&tmE, 0, k, tn * 128, p.e_batched ? bn : 0);
-            tma_prefetch_4d(&tmE, 32, k, tn * 128, p.e_batched ? bn : 0);
+            tma_prefetch_4d(&tmE, 0, k, rn, p.e_batched ? bn : 0);
+            tma_prefetch_4d(&tmE, 32, k, rn, p.e_batched ? bn : 0);
           }
         }
         for (int m = 0; m <= d; ++m, ++i) {
@@ -252,6 +254,31 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     const uint64_t pol_keep = policy_evict_last();
     const int gt = (warp - W_GA) * 32 + lane;
     const int grp4 = gt & 31, jb = gt >> 5;
+    // Store the staged aggregate of tile (bp, tp) from window buffer `buf`.  A full tile (or the last one: rows past
+    // the tensor end are clipped) leaves through one TMA tensor store issued by thread 0; a tile cut short by the
+    // window limit must not touch the rows of the next tile: its rows are copied by the 64 threads of this group.
+    auto store_tile = [&](int buf, int bp, int tp, bool wait_read) {
+      const int ra = __ldg(p.r0 + tp), rb = __ldg(p.r0 + tp + 1);
+      const int nrec = rb - ra;
+      const uint32_t src = sbase + OFF_WIN + buf * 2 * BLK;
+      if (nrec == 128 || rb >= p.n_rec) {
+        if (gt == 0) {
+          tma_store_3d(&tmOut, src, 0, ra, bp);
+          tma_store_3d(&tmOut, src + BLK, 32, ra, bp);
+          bulk_commit();
+          if (wait_read) bulk_wait_read0();
+        }
+      } else {
+        const uint8_t* sm = smem + OFF_WIN + buf * 2 * BLK;
+        float* out = p.aggr + ((long long)bp * p.n_rec + ra) * 64;
+        for (int i = gt; i < nrec * 16; i += 64) {  // 16 chunks of 16 bytes per 256-byte row
+          const int r = i >> 4, ch = i & 15;
+          const float4 v = *reinterpret_cast<const float4*>(sm + (ch >> 3) * BLK + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+          *reinterpret_cast<float4*>(out + (long long)r * 64 + ch * 4) = v;
+        }
+        fence_proxy_async();  // the buffer is refilled by TMA gathers next
+      }
+    };
     for (int ti = 0; ti < n_my; ++ti) {
       const int w = blockIdx.x + ti * gridDim.x;
       int b, t;
@@ -260,21 +287,17 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       int4 ids = make_int4(0, 0, 0, 0);
       if (grp4 < ngrp) ids = __ldg(reinterpret_cast<const int4*>(p.win_u + (size_t)t * 128) + grp4);
       const uint32_t full = bar_win_full + 8 * (ti & 1);
-      if (gt == 0) {
-        if (ti >= 2) {
-          // the buffer holds the staged aggregate of tile ti-2: store it, then reuse the buffer
-          const int wp = w - 2 * gridDim.x;
-          int bp, tp;
-          work_bt(wp, bp, tp);
-          mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)(((ti - 2) >> 1) & 1));
-          const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
-          tma_store_3d(&tmOut, src, 0, tp * 128, bp);
-          tma_store_3d(&tmOut, src + BLK, 32, tp * 128, bp);
-          bulk_commit();
-          bulk_wait_read0();
-        }
-        mbar_expect_tx(full, (uint32_t)ngrp * 1024u);
+      if (ti >= 2) {
+        // the buffer holds the staged aggregate of tile ti-2: store it, then reuse the buffer
+        const int wp = w - 2 * gridDim.x;
+        int bp, tp;
+        work_bt(wp, bp, tp);
+        if (gt == 0) mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)(((ti - 2) >> 1) & 1));
+        named_bar_sync(12, 64);
+        store_tile(ti & 1, bp, tp, true);
+        named_bar_sync(12, 64);
       }
+      if (gt == 0) mbar_expect_tx(full, (uint32_t)ngrp * 1024u);
       named_bar_sync(12, 64);
       if (grp4 < ngrp) {
         const int boff = p.ps_rows * b;
@@ -282,19 +305,15 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
                     ids.y + boff, ids.z + boff, ids.w + boff, pol_keep);
       }
     }
-    if (gt == 0) {
-      for (int ti = (n_my >= 2 ? n_my - 2 : 0); ti < n_my; ++ti) {  // the last tiles' aggregates
-        const int w = blockIdx.x + ti * gridDim.x;
-        int b, t;
-        work_bt(w, b, t);
-        mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
-        const uint32_t src = sbase + OFF_WIN + (ti & 1) * 2 * BLK;
-        tma_store_3d(&tmOut, src, 0, t * 128, b);
-        tma_store_3d(&tmOut, src + BLK, 32, t * 128, b);
-        bulk_commit();
-      }
-      bulk_wait0();
+    for (int ti = (n_my >= 2 ? n_my - 2 : 0); ti < n_my; ++ti) {  // the last tiles' aggregates
+      const int w = blockIdx.x + ti * gridDim.x;
+      int b, t;
+      work_bt(w, b, t);
+      if (gt == 0) mbar_wait(bar_staged + 8 * (ti & 1), (uint32_t)((ti >> 1) & 1));
+      named_bar_sync(12, 64);
+      store_tile(ti & 1, b, t, false);
     }
+    if (gt == 0) bulk_wait0();
   } else if (warp == W_MMA) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
@@ -391,8 +410,9 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
     // window row of this thread's edge of neighbour slot k of receiver tile t (prefetched one sub-tile ahead)
     auto load_loc = [&](int t, int k) -> int {
-      const long long r = (long long)t * 128 + row;
-      return (r < p.n_rec) ? (int)__ldg(p.loc + r * d + k) : 0;
+      const int ra = __ldg(p.r0 + t);
+      const long long r = (long long)ra + row;
+      return (r < __ldg(p.r0 + t + 1)) ? (int)__ldg(p.loc + r * d + k) : 0;
     };
     // SiLU(z) = h + h*tanh(h) with h = z/2: halve the first-Linear weight tiles once (exact), so the GEMMs
     // deliver h's terms directly; the gathered sender term (which carries b1) is halved in the FMA below
@@ -635,7 +655,7 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   p.mean = (flags & NLAM_AGGR_MEAN) ? 1 : 0;
   p.n_rec = nr;
   p.B = B;
-  p.n_tiles = (int)((nr + 127) / 128);
+  p.n_tiles = g->ell_nt;
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
   const long long n_work = (long long)p.n_tiles * p.B;
@@ -675,6 +695,7 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     q.n_rec = p.n_rec;
     q.B = p.B;
     q.n_tiles = p.n_tiles;
+    q.r0 = g->ell_r0;
     q.dbg = p.dbg;
     static int pf = -1;
     if (pf < 0) pf = getenv("NLAM_ELL_NO_PREFETCH") ? 0 : 1;
