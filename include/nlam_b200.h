@@ -136,12 +136,20 @@ size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, int flags);
 /* One InteractionNet / PropagationNet forward.  `edge` and `edge_out` are in CSR edge order
  * (nlam_graph_perm); send (B,Ns,H), rec (B,Nr,H), edge (B,E,H), rec_out (B,Nr,H),
  * edge_out (B,E,H) or NULL (update_edges=False).  aggr_out (B,Nr,H) may be NULL (then it
- * lives in the workspace); out strides are dense. */
+ * lives in the workspace); out strides are dense.
+ * edge_out may ALIAS edge (e' written over e: the middle layers of a processor stack whose intermediate edge tensors
+ * nobody else reads) only for the call shapes nlam_inet_inplace_supported reports; aliasing is an error otherwise. */
 int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
                   const float* send, int64_t send_bstride, const float* rec, int64_t rec_bstride,
                   const float* edge, int64_t edge_bstride, float* rec_out, float* edge_out,
                   float* aggr_out, int B, int flags, void* workspace, size_t ws_bytes,
                   void* stream);
+
+/* 1 if nlam_inet_fwd with these arguments may be called with edge_out == edge (tensor-core path with node projections on a
+ * general CSR edge set, dense batches: the update is a TMA reduce-add of the message tiles, csrc/tc8.cu), else 0. */
+int nlam_inet_inplace_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bstride,
+                                const float* rec, int64_t rec_bstride, const float* edge, int64_t edge_bstride, int B,
+                                int flags);
 
 /* out[b,r,:] = (res ? res[b, ridx ? ridx[r] : r, :] : 0) + MLP(concat_s src_s[b, idx_s[r], :])
  * for r in [0,n_rows); out2 (nullable) = res2[b,r,:] + out[b,r,:]. */

@@ -77,6 +77,24 @@ extern "C" size_t nlam_inet_workspace_bytes(const NlamGraph* g, int B, int H, in
   return rup256((size_t)B * g->n_rec * H * sizeof(float)) + need;
 }
 
+// the call shapes that take tc_edge_rmw (tc8.cu) when edge_out aliases edge
+static bool inplace_path(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                         int64_t rec_bs, const float* edge, int64_t edge_bs, int B, int flags) {
+  const int H = edge_mlp->out_dim[edge_mlp->n_linear - 1];
+  if (!(want_tf32(flags) && tc_edge_supported(g, edge_mlp, flags))) return false;
+  const int64_t send_rows = (B > 1 && send_bs > 0) ? send_bs / H : g->n_send;
+  if (tc_ell_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, true)) return false;
+  if (!tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows)) return false;
+  return tc_edge_rmw_supported(g, edge, edge_bs, edge, B);
+}
+
+extern "C" int nlam_inet_inplace_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs,
+                                           const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs, int B,
+                                           int flags) {
+  if (!g || !edge_mlp || !send || !rec || !edge || B < 1 || edge_mlp->n_linear < 1) return 0;
+  return inplace_path(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, B, flags) ? 1 : 0;
+}
+
 extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
                              const float* send, int64_t send_bs, const float* rec, int64_t rec_bs,
                              const float* edge, int64_t edge_bs, float* rec_out, float* edge_out,
@@ -88,6 +106,9 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   NLAM_REQUIRE(edge_mlp->in_dim == 3 * H && aggr_mlp->in_dim == 2 * H &&
                    aggr_mlp->out_dim[aggr_mlp->n_linear - 1] == H,
                NLAM_E_INVALID, "nlam_inet_fwd: MLP widths inconsistent with H=%d", H);
+  NLAM_REQUIRE(edge_out != edge || inplace_path(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, B, flags),
+               NLAM_E_INVALID, "nlam_inet_fwd: edge_out aliases edge for a call shape without in-place support "
+               "(see nlam_inet_inplace_supported)");
   cudaStream_t st = (cudaStream_t)stream;
   const int mean = (flags & (NLAM_AGGR_MEAN | NLAM_PROPAGATION)) ? 1 : 0;  // PropagationNet forces mean
   const bool prop = flags & NLAM_PROPAGATION;
@@ -119,7 +140,11 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
       rc = tc_ell_edge(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, aggr, B, flags, st, scratch);
     } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows)) {
       // split first Linear: node projections + K=64 edge kernel with sender windows (tc5.cu)
-      rc = tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
+      // (tc8.cu when the edge tensor is updated in place or not written at all)
+      if (tc_edge_rmw_supported(g, edge, edge_bs, edge_out, B))
+        rc = tc_edge_rmw(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
+      else
+        rc = tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
     } else if (tc_edge_bcast_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs, B, edge_out != nullptr)) {
       // batch-broadcast edge features and receivers, large sender set, no edge update (grid -> mesh): tile-major
       // kernel with the edge term resident in TMEM and raw sender rows gathered (tc6.cu)

@@ -128,6 +128,11 @@ int tc_edge_bcast(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
              cudaStream_t stream, float* ws);
+// tc8.cu: same math, edge tensor updated in place (TMA reduce-add) or not written at all
+bool tc_edge_rmw_supported(const NlamGraph* g, const float* edge, int64_t edge_bs, const float* edge_out, int B);
+int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
+                cudaStream_t stream, float* ws);
 // tc4.cu
 bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
 bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows);

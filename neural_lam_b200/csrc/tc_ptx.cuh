@@ -123,6 +123,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// e'[box] += smem tile (fp32 add performed in L2; element type and swizzle come from the tensor map)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -16,9 +16,9 @@ from . import _lib, backward, ops
 from .networks import _aten_forward, make_mlp
 
 _DEFAULT_MATH = "auto"
-# in-place edge update of the middle layers of a stack: needs an edge kernel whose stores never touch rows of a
-# neighbouring tile (the reduce-add store of the v4 edge kernel); off while the library has none
-_INPLACE_EDGE_UPDATE = False
+# in-place edge update of the middle layers of a no-grad stack (csrc/tc8.cu: TMA reduce-add of the message tiles); the
+# library decides per call shape (nlam_inet_inplace_supported), other shapes stay out of place
+_INPLACE_EDGE_UPDATE = True
 _MATH_FLAGS = {"auto": 0, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}
 
 

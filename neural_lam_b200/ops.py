@@ -317,7 +317,9 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     em = mlp_struct(edge_seq)
     am = mlp_struct(aggr_seq)
     rec_out = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32)
-    if update_edges and edge_inplace and Be == B and (B == 1 or ebs == graph.n_edges * H):
+    if (update_edges and edge_inplace and Be == B and (B == 1 or ebs == graph.n_edges * H)
+            and L.nlam_inet_inplace_supported(graph.handle, ctypes.byref(em), s.data_ptr(), sbs, r.data_ptr(), rbs,
+                                              e.data_ptr(), ebs, B, flags)):
         edge_out = e
     else:
         edge_out = torch.empty((B, graph.n_edges, H), device=dev, dtype=torch.float32) if update_edges else None

@@ -436,3 +436,82 @@ def test_fused_output_map_step_epilogue(with_boundary):
         assert torch.equal(got.cpu()[:, sel], bnd[:, sel])
     # the exact-fp32 mode does not fuse: callers fall back to the two kernels
     assert ops.rowmlp_step(m, x.to(DEV), prev.to(DEV), None, None, std.to(DEV), mean.to(DEV), flags=_lib.MATH_FP32) is None
+
+
+RMW_CASES = [
+    # name, n nodes, n edges, B
+    ("small_b1", 60, 500, 1),
+    ("ragged_b3", 300, 2600, 3),
+    ("empty_receivers", 900, 700, 2),
+    ("many_items", 4000, 36000, 5),   # > 148 work items: CTA ranges start in the middle of a tile's batches
+    ("deg100", 40, 4000, 4),
+]
+
+
+@pytest.mark.parametrize("case", RMW_CASES, ids=[c[0] for c in RMW_CASES])
+def test_inplace_edge_update_kernel(case):
+    """tc8.cu: e += m as a TMA reduce-add of the staged message tiles (edge_out aliases edge) and the no-edge-output
+    mode, against the out-of-place kernel (tc5.cu) on the same inputs and against the fp64 oracle."""
+    name, nn_, ne, B = case
+    ei = _graph(nn_, nn_, ne, 3, True)
+    torch.manual_seed(1)
+    net = nlb.InteractionNet(ei, 64, update_edges=True, math="tf32")
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, nn_, 64)
+    edge = torch.randn(B, ne, 64)
+    want = rp.interaction_net({k: v.double() for k, v in net.state_dict().items()}, ei, x.double(), x.double(),
+                              edge.double(), update_edges=True)
+    net = net.to(DEV)
+    g = net._graph(torch.device(DEV, torch.cuda.current_device()))
+    xs, e0 = x.to(DEV), edge.to(DEV)
+    flags = net._flags()
+    with torch.no_grad():
+        with ops.profile_launches() as prof:
+            rec_a, edge_a, _ = ops.inet_fwd(g, net.edge_mlp, net.aggr_mlp, xs, xs, e0, True, flags)  # out of place
+        assert "tc_edge3_kernel" in prof.names(), prof.names()
+        e_in = e0.clone()
+        with ops.profile_launches() as prof:
+            rec_b, edge_b, _ = ops.inet_fwd(g, net.edge_mlp, net.aggr_mlp, xs, xs, e_in, True, flags, edge_inplace=True)
+        assert "tc_edge_rmw_kernel" in prof.names(), prof.names()
+        assert edge_b.data_ptr() == e_in.data_ptr()
+        with ops.profile_launches() as prof:
+            rec_c, edge_c, _ = ops.inet_fwd(g, net.edge_mlp, net.aggr_mlp, xs, xs, e0, False, flags)  # no edge output
+        assert "tc_edge_rmw_kernel" in prof.names() and edge_c is None
+    torch.cuda.synchronize()
+    # same TF32 products; only fp32 summation orders differ between the kernels
+    assert (edge_b - edge_a).abs().max().item() <= 2e-5
+    assert (rec_b - rec_a).abs().max().item() <= 1e-4
+    assert (rec_c - rec_a).abs().max().item() <= 1e-4
+    err = max((rec_b.double().cpu() - want[0]).abs().max().item(), (edge_b.double().cpu() - want[1]).abs().max().item())
+    assert err <= ABS_TOL, (name, err)
+    # a batch-broadcast edge tensor can not be updated in place: the library must refuse the alias
+    if B > 1:
+        eb = e0[:1].expand(B, -1, -1)
+        with torch.no_grad():
+            _, edge_d, _ = ops.inet_fwd(g, net.edge_mlp, net.aggr_mlp, xs, xs, eb, True, flags, edge_inplace=True)
+        assert edge_d.data_ptr() != eb.data_ptr()
+
+
+def test_stack_updates_private_edge_tensor_in_place():
+    """GNNSequential with keep_edge_rep=False (GraphLAM.process_step): first layer out of place (its input is the
+    caller's), middle layers in place, last layer without edge output — same values as the plain layer-by-layer
+    evaluation, input untouched."""
+    from neural_lam_b200.networks import make_gnn_seq
+    ei = _graph(500, 500, 4500, 5, True)
+    torch.manual_seed(2)
+    seq = make_gnn_seq(ei, 4, 1, 64).to(DEV)
+    x = torch.randn(3, 500, 64, device=DEV)
+    e_static = torch.randn(1, 4500, 64, device=DEV)
+    e_in = e_static.expand(3, -1, -1)
+    keep = e_static.clone()
+    with torch.no_grad():
+        want, _ = seq(x, e_in, keep_edge_rep=True)
+        with ops.profile_launches() as prof:
+            got, e_none = seq(x, e_in, keep_edge_rep=False)
+    assert e_none is None
+    assert prof.names().count("tc_edge_rmw_kernel") == 3 and prof.names().count("tc_edge3_kernel") == 1, prof.names()
+    assert torch.equal(e_static, keep)
+    assert (got - want).abs().max().item() <= 2e-4
