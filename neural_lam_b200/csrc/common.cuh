@@ -135,7 +135,8 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
                 cudaStream_t stream, float* ws);
 // tc4.cu
 bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
-bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows);
+bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows, const float* out,
+                                    const StepEpilogue* ep);
 int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows,
                 int B, cudaStream_t stream, const StepEpilogue* ep = nullptr);
 // tc3.cu

@@ -875,7 +875,7 @@ int tc_rowmlp(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamR
   NLAM_REQUIRE(aligned16(out), NLAM_E_INVALID, "tc_rowmlp: output not 16-byte aligned");
   // dense 64-wide inputs, LayerNorm output: the streaming kernel of tc4.cu
   if (!ep && tc_rowmlp64_supported(mlp, srcs, n_src, res, n_rows)) return tc_rowmlp64(mlp, srcs, n_src, res, out, n_rows, B, st);
-  if (!res && tc_rowmlp_narrow_out_supported(mlp, srcs, n_src, n_rows)) return tc_rowmlp64(mlp, srcs, n_src, nullptr, out, n_rows, B, st, ep);
+  if (!res && tc_rowmlp_narrow_out_supported(mlp, srcs, n_src, n_rows, out, ep)) return tc_rowmlp64(mlp, srcs, n_src, nullptr, out, n_rows, B, st, ep);
   TcParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap a0, a1, w1, w2;

@@ -30,7 +30,7 @@ namespace nlam {
 namespace r4 {
 constexpr int THREADS = 640;
 constexpr int EPI = 256;
-constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_ST = 18, W_RP2 = 19;  // W_RP2: second repack warp (narrow inputs)
+constexpr int W_E1 = 8, W_MMA = 16, W_RING = 17, W_ST = 18;  // warp 19 idle
 constexpr int NR = 5;   // ring slots
 constexpr int NT = 3;   // TMEM stages
 constexpr uint32_t BLK = 16384;
@@ -106,6 +106,8 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 256);  // gamma | beta   (narrow output: std | mean)
   int2* ctab = reinterpret_cast<int2*>(smem + OFF_MISC + 1024);    // narrow inputs: column cc of the operand tile =
                                                                    // staging[ctab.x + row * ctab.y] (ctab.x < 0: zero)
+  float* sb2 = reinterpret_cast<float*>(smem + OFF_MISC + 768);     // narrow output: b2 (zero past the output width)
+  const uint32_t bar_ep_full = mb + 1536;  // [3] narrow output: prev / boundary / mask slabs of the tile landed (tx bytes)
   const int n_src = p.n_src;
   const int nb1 = 2 * n_src;
 
@@ -114,12 +116,12 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_init(bar_w, 1);
       mbar_init(bar_wscaled, EPI);
       for (int t = 0; t < NR; ++t) {
-        mbar_init(bar_ring_full + 8 * t, p.in_narrow ? 64 : 1);  // repack threads / TMA transactions
+        mbar_init(bar_ring_full + 8 * t, p.in_narrow ? EPI : 1);  // repack threads / TMA transactions
         mbar_init(bar_ring_free + 8 * t, 1);
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(bar_st_full + 8 * t, 1);
-        mbar_init(bar_st_free + 8 * t, 64);
+        mbar_init(bar_st_free + 8 * t, EPI);
       }
       for (int t = 0; t < NT; ++t) {
         mbar_init(bar_d1_full + 8 * t, 1);
@@ -127,6 +129,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         mbar_init(bar_d2_full + 8 * t, 1);
         mbar_init(bar_d_free + 8 * t, EPI);
         mbar_init(bar_staged + 8 * t, EPI);
+        mbar_init(bar_ep_full + 8 * t, 1);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -157,6 +160,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
     ctab[tid] = e;
   }
+  if (tid < 64) sb2[tid] = (p.out_narrow && tid < p.out_narrow) ? p.b2[tid] : 0.f;
   if (tid < 64) {
     if (p.out_narrow) {
       sprm[tid] = (p.ep_prev && tid < p.out_narrow) ? p.ep_std[tid] : 1.f;
@@ -179,33 +183,31 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   auto op_phase = [&](int ti, int s) -> uint32_t {
     return (uint32_t)(p.in_narrow ? (ti / 3) & 1 : ((ti * n_src + s) / NR) & 1);
   };
-  // narrow inputs: thread rt (0..63, warps 17 and 19) repacks rows rt and rt+64 of tile ti from the flat staging slot
-  // into the K-major swizzled operand tile; columns k_real..63 are zero
-  auto repack_tile = [&](int ti, int rt) {
+  // narrow inputs: the 256 threads of the epilogue-1 group repack tile ti from the flat staging slot into the K-major
+  // swizzled operand tile (thread = row x one 32-column block; columns k_real..63 are zero).  Two warps did this before:
+  // 450 instructions per thread and tile in series, 6.2 k cycles per tile — the whole kernel waited for them.
+  auto repack_tile = [&](int ti, int gt, bool lead) {
     const int st = ti & 1;
     const int slot = op_slot(ti, 0);
-    if (rt == 0) {
+    if (lead) {
       mbar_wait(bar_st_full + 8 * st, (uint32_t)((ti >> 1) & 1));
       mbar_wait(bar_ring_free + 8 * slot, op_phase(ti, 0) ^ 1u);
     }
-    named_bar_sync(12, 64);
+    named_bar_sync(1, EPI);
     uint8_t* tile = smem + OFF_RING + slot * 2 * BLK;
     const float* stg = reinterpret_cast<const float*>(smem + OFF_RING + st * 2 * BLK);
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = rt + 64 * rr;
-      const int rx = row & 7;
+    const int row = gt & 127, hh = gt >> 7;
+    const int rx = row & 7;
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {  // one 16-byte chunk of the operand row per store
-        float4 o;
-        float* ov = reinterpret_cast<float*>(&o);
+    for (int ch = 0; ch < 8; ++ch) {  // one 16-byte chunk of the operand row per store
+      float4 o;
+      float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int2 e = ctab[4 * ch + u];  // broadcast read
-          ov[u] = (e.x >= 0) ? stg[e.x + row * e.y] : 0.f;  // lane stride d floats: conflict-free for odd d
-        }
-        *reinterpret_cast<float4*>(tile + (ch >> 3) * BLK + row * 128 + (((ch & 7) ^ rx) << 4)) = o;
+      for (int u = 0; u < 4; ++u) {
+        const int2 e = ctab[32 * hh + 4 * ch + u];  // broadcast read
+        ov[u] = (e.x >= 0) ? stg[e.x + row * e.y] : 0.f;  // lane stride d floats: conflict-free for odd d
       }
+      *reinterpret_cast<float4*>(tile + hh * BLK + row * 128 + ((ch ^ rx) << 4)) = o;
     }
     fence_proxy_async();  // generic writes -> tcgen05.mma operand reads
     mbar_arrive(bar_ring_full + 8 * slot);
@@ -238,10 +240,9 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
       }
     }
-    if (p.in_narrow) {
-      // ---- narrow inputs: bulk copies into the staging slots (lane 0, one tile ahead) + repack (warps 17 and 19)
-      const int rt = lane;  // this thread repacks rows rt and rt + 64 (+32 for the second warp)
-      auto issue = [&](int ti) {
+    if (p.in_narrow && lane == 0) {
+      // ---- narrow inputs: bulk copies into the two staging slots (ring slots 0/1), as far ahead as they are free
+      for (int ti = 0; ti < n_my; ++ti) {
         const int w = blockIdx.x + ti * gridDim.x;
         const int b = w / p.n_tiles, t = w - b * p.n_tiles;
         const int st = ti & 1;
@@ -256,17 +257,8 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           dst += (uint32_t)(128 * d * 4);
         }
         R4_DBG(0, ti);
-      };
-      if (lane == 0 && n_my > 0) issue(0);
-      for (int ti = 0; ti < n_my; ++ti) {
-        if (lane == 0 && ti + 1 < n_my) issue(ti + 1);
-        __syncwarp();
-        repack_tile(ti, rt);
       }
     }
-  } else if (warp == W_RP2) {
-    if (p.in_narrow)
-      for (int ti = 0; ti < n_my; ++ti) repack_tile(ti, 32 + lane);
   } else if (warp == W_ST) {
     // =============================== output stores ===============================
     if (lane == 0 && !p.out_narrow) {
@@ -279,6 +271,23 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const uint32_t src = sbase + OFF_RING + slot * 2 * BLK;
         tma_store_3d(&tmOut, src, 0, t * 128, b);
         tma_store_3d(&tmOut, src + BLK, 32, t * 128, b);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(bar_ring_free + 8 * slot);
+        R4_DBG(7, ti);
+      }
+      bulk_wait0();
+    }
+    if (lane == 0 && p.out_narrow) {
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int ts = ti % NT;
+        const int slot = op_slot(ti, p.out_src);
+        const int nrows = (int)min(128LL, p.n_rows - (long long)t * 128);
+        mbar_wait(bar_staged + 8 * ts, (uint32_t)((ti / NT) & 1));
+        bulk_store_1d(p.out + ((long long)b * p.n_rows + (long long)t * 128) * p.out_narrow,
+                      sbase + OFF_RING + slot * 2 * BLK + 18432, (uint32_t)(nrows * p.out_narrow * 4));
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(bar_ring_free + 8 * slot);
@@ -382,9 +391,31 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       fence_proxy_async();
       mbar_arrive(bar_wscaled);
     }
+    const int gt1 = tid - W_E1 * 32;
+    if (p.in_narrow) {  // operand tiles are repacked two tiles ahead of their SiLU
+      if (n_my > 0) repack_tile(0, gt1, lead);
+      if (n_my > 1) repack_tile(1, gt1, lead);
+    }
     for (int ti = 0; ti < n_my; ++ti) {
       const int ts = ti % NT;
       if (lead) mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((ti / NT) & 1));
+      if (lead && lane == 0 && p.out_narrow && p.ep_prev) {
+        // narrow output + step epilogue: the first GEMM has consumed the operand tile, so its slot can already take
+        // the prev / boundary / mask slabs of this tile (contiguous in global memory: one bulk copy each)
+        const int w = blockIdx.x + ti * gridDim.x;
+        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        const int nrows = (int)min(128LL, p.n_rows - (long long)t * 128);
+        const uint32_t bytes = (uint32_t)(nrows * p.out_narrow * 4);
+        const uint32_t dst = sbase + OFF_RING + op_slot(ti, p.out_src) * 2 * BLK;
+        const long long g0 = ((long long)b * p.n_rows + (long long)t * 128) * p.out_narrow;
+        const uint32_t bar = bar_ep_full + 8 * ts;
+        mbar_expect_tx(bar, p.ep_bnd ? 2u * bytes + (uint32_t)(nrows * 4) : bytes);
+        bulk_load_1d(dst, p.ep_prev + g0, bytes, bar);
+        if (p.ep_bnd) {
+          bulk_load_1d(dst + 9216, p.ep_bnd + g0, bytes, bar);
+          bulk_load_1d(dst + 27648, p.ep_mask + (long long)t * 128, (uint32_t)(nrows * 4), bar);
+        }
+      }
       named_bar_sync(1, EPI);
       tc_fence_after();
       if (lead && lane == 0) R4_DBG(4, ti);
@@ -401,6 +432,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       tmem_st32(d1 + 64, v);
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
+      if (p.in_narrow && ti + 2 < n_my) repack_tile(ti + 2, gt1, lead);
     }
   } else if (warp < W_E1) {
     // =============================== epilogue 2: bias, LayerNorm, residual; output in place over the source tile ===
@@ -419,83 +451,49 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int nb = p.out_narrow ? p.out_narrow : 64;
       b2r[i] = make_float2(c < nb ? __ldg(p.b2 + c) : 0.f, c + 1 < nb ? __ldg(p.b2 + c + 1) : 0.f);
     }
-    // narrow output: (row, column) of this thread's first element of a tile and the step of 256 elements
-    const int nout_ = p.out_narrow ? p.out_narrow : 1;
-    const int er0 = tid / nout_, ec0 = tid - er0 * nout_, eq = EPI / nout_, em = EPI - eq * nout_;
     for (int ti = 0; ti < n_my; ++ti) {
       const int ts = ti % NT;
       const int slot = op_slot(ti, p.out_src);
       if (p.out_narrow) {
-        // ---- narrow output (+ forecast-step epilogue): out = A + S*y with A, S from prev / boundary / mask / std /
-        // mean, loaded BEFORE the wait for the accumulators so that no L2 round trip sits in the tile's critical path
-        const int w = blockIdx.x + ti * gridDim.x;
-        const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+        // ---- narrow output (+ forecast-step epilogue), bulk-copy form: prev / boundary / mask of the tile sit in the
+        // (dead) operand slot, this thread finishes columns [9*half, 9*half + 9) of its row into the flat output slab,
+        // which leaves by one bulk store — no global access and no index arithmetic in the epilogue threads (the
+        // element-wise form below executes 8 k warp instructions per tile, this one ~1 k)
         const int nout = p.out_narrow;
-        const int n = (int)min(128LL, p.n_rows - (long long)t * 128) * nout;
-        const long long g0 = ((long long)b * p.n_rows + (long long)t * 128) * nout;
-        float ea[9], es[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-          ea[j] = 0.f;
-          es[j] = 1.f;
+        if (warp == 0) {
+          mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
+          if (p.ep_prev) mbar_wait(bar_ep_full + 8 * ts, (uint32_t)((ti / NT) & 1));
         }
-        if (p.ep_prev) {
-          // all loads first (independent, in flight together), arithmetic afterwards; element i = tid + 256*j of the
-          // tile is (row, column) = (er0, ec0) advanced j times by 256 = eq*nout + em (no divisions in the loop)
-          float pv[9], bd[9], mk[9];
-          int r = er0, c = ec0;
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            const int i = tid + EPI * j;
-            const bool act = i < n;
-            pv[j] = act ? __ldg(p.ep_prev + g0 + i) : 0.f;
-            bd[j] = (act && p.ep_bnd) ? __ldg(p.ep_bnd + g0 + i) : 0.f;
-            mk[j] = (act && p.ep_bnd) ? __ldg(p.ep_mask + (long long)t * 128 + r) : 0.f;
-            c += em;
-            r += eq;
-            if (c >= nout) {
-              c -= nout;
-              ++r;
-            }
-          }
-          c = ec0;
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            if (tid + EPI * j < n) {
-              ea[j] = mk[j] * bd[j] + (1.0f - mk[j]) * (pv[j] + sprm[64 + c]);
-              es[j] = (1.0f - mk[j]) * sprm[c];
-            }
-            c += em;
-            if (c >= nout) c -= nout;
-          }
-        }
-        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
         named_bar_sync(2, EPI);
         tc_fence_after();
         if (tid == 0) R4_DBG(5, ti);
-        float* flat = reinterpret_cast<float*>(smem + OFF_RING + slot * 2 * BLK);  // GEMM1 has consumed the operand tile
-        if (half == 0) {
-          float vf[32];
-          tmem_ld32(tmem_base + ts * 128 + t_lane, vf);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (2 * i < nout) flat[row * nout + 2 * i] = vf[2 * i] + b2r[i].x;  // pitch nout floats: conflict-free for odd nout
-            if (2 * i + 1 < nout) flat[row * nout + 2 * i + 1] = vf[2 * i + 1] + b2r[i].y;
-          }
-        }
+        const float* s_prev = reinterpret_cast<const float*>(smem + OFF_RING + slot * 2 * BLK);
+        const float* s_bnd = s_prev + 2304;
+        float* s_out = const_cast<float*>(s_prev) + 4608;
+        const float* s_mask = s_prev + 6912;
+        float vv[16];
+        tmem_ld16(tmem_base + ts * 128 + t_lane + (half ? 8 : 0), vv);  // half 1: columns 8..23, it uses 9..17
         tc_fence_before();
         mbar_arrive(bar_d_free + 8 * ts);
-        named_bar_sync(3, EPI);  // flat tile complete
+        const float mk = (p.ep_prev && p.ep_bnd) ? s_mask[row] : 0.f;
+        const float om = 1.0f - mk;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
-          const int i = tid + EPI * j;
-          if (i < n) p.out[g0 + i] = fmaf(es[j], flat[i], ea[j]);
+          const int c = 9 * half + j;
+          if (c < nout) {
+            const float y = (half ? vv[j + 1] : vv[j]) + sb2[c];
+            float o = y;
+            if (p.ep_prev) {
+              const float pv = s_prev[row * nout + c];  // row pitch nout floats: conflict-free for odd nout
+              const float bd = p.ep_bnd ? s_bnd[row * nout + c] : 0.f;
+              o = fmaf(om * sprm[c], y, mk * bd + om * (pv + sprm[64 + c]));
+            }
+            s_out[row * nout + c] = o;
+          }
         }
-        named_bar_sync(3, EPI);  // flat tile consumed: the slot may be refilled
-        if (tid == 0) {
-          mbar_arrive(bar_ring_free + 8 * slot);
-          R4_DBG(6, ti);
-        }
+        fence_proxy_async();
+        mbar_arrive(bar_staged + 8 * ts);
+        if (tid == 0) R4_DBG(6, ti);
         continue;
       }
       if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
@@ -600,12 +598,16 @@ bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src
   return true;
 }
 
-// narrow output (<= 18 columns, no LayerNorm, no residual), optionally with the forecast-step epilogue
-bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows) {
+// narrow output (<= 18 columns, no LayerNorm, no residual), optionally with the forecast-step epilogue.  The output slab
+// of a tile (and prev / boundary / mask) travels by 1-D bulk copies: rows a multiple of 4, 16-byte aligned tensors.
+bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows, const float* out,
+                                    const StepEpilogue* ep) {
   if (!row64_enabled()) return false;
   int nout = 0;
   if (n_rows < 1 || n_rows >= (1LL << 31) - 256) return false;
   if (!mlp_shape_ok(mlp, &nout) || nout > 18 || mlp->ln_gamma) return false;
+  if (n_rows % 4 != 0 || !aligned16(out)) return false;
+  if (ep && !(aligned16(ep->prev) && (!ep->boundary || (aligned16(ep->boundary) && aligned16(ep->mask))))) return false;
   return row64_input_kind(mlp, srcs, n_src, n_rows) != 0;
 }
 

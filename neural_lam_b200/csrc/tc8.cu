@@ -73,6 +73,7 @@ struct Edge8Params {
     if (p.dbg && blockIdx.x == 1 && (it) >= 40 && (it) < 56) p.dbg[((it) - 40) * 16 + (slot)] = clock64(); \
   } while (0)
 
+template <bool RNOW>
 __global__ void __launch_bounds__(e8::THREADS, 1)
 tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
@@ -443,7 +444,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
       if (gt == 0) E8_DBG(4, it);
-      if (prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
+      if (!RNOW && prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
 
       // ---- epilogue 2: bias, LayerNorm -> messages into the item's window slot (epilogue 1 has consumed the window)
       if (lane == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((it / NT) & 1));
@@ -502,13 +503,17 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
       if (p.has_out) fence_proxy_async();
       mbar_arrive(bar_staged + 8 * (it % 6));
       if (gt == 0) E8_DBG(6, it);
+      if (RNOW) {  // measured slower (269 vs 254 us): the group idles while the second GEMM runs
+        reduce_item(it, sw, b, r0_cur, nrec_cur);
+        continue;
+      }
       prev_it = it;
       prev_sw = sw;
       prev_b = b;
       prev_r0 = r0_cur;
       prev_nrec = nrec_cur;
     }
-    if (prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
+    if (!RNOW && prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
   }
 
   tc_fence_before();
@@ -586,13 +591,19 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   int dev = 0;
   NLAM_CUDA_OK(cudaGetDevice(&dev));
   if (!(attr_mask & (1u << (dev & 31)))) {
-    NLAM_CUDA_OK(cudaFuncSetAttribute(tc_edge_rmw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e8::SMEM));
+    NLAM_CUDA_OK(cudaFuncSetAttribute(tc_edge_rmw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e8::SMEM));
+    NLAM_CUDA_OK(cudaFuncSetAttribute(tc_edge_rmw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e8::SMEM));
     attr_mask |= 1u << (dev & 31);
   }
   const long long n_work = (long long)p.n_tiles * p.B;
   NLAM_REQUIRE(n_work < (1LL << 30), NLAM_E_UNSUPPORTED, "tc_edge_rmw: too many work items");
   const int sms = num_sms();
   p.items_per_cta = (int)((n_work + sms - 1) / sms);
+  static int rnow = -1;
+  if (rnow < 0) {
+    const char* e = getenv("NLAM_E8_RNOW");
+    rnow = e ? atoi(e) : 0;
+  }
   const int grid = (int)((n_work + p.items_per_cta - 1) / p.items_per_cta);
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
@@ -604,7 +615,11 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   }
   {
     ProfScope ps("tc_edge_rmw_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
-    tc_edge_rmw_kernel<<<grid, e8::THREADS, e8::SMEM, st>>>(me, mw1, mw2, me, mps, p);
+    // RNOW: segmented sum of an item right after its epilogue 2 (else after epilogue 1 of the group's next item)
+    if (rnow)
+      tc_edge_rmw_kernel<true><<<grid, e8::THREADS, e8::SMEM, st>>>(me, mw1, mw2, me, mps, p);
+    else
+      tc_edge_rmw_kernel<false><<<grid, e8::THREADS, e8::SMEM, st>>>(me, mw1, mw2, me, mps, p);
   }
   count_launch();
   if (dbg_on) {

@@ -135,6 +135,10 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 1-D bulk copy shared -> global (16-byte aligned addresses, size a multiple of 16), bulk-group completion
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -145,6 +149,11 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint64_t pol) {
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+// arrive on an mbarrier once all cp.async of this thread issued so far have landed (the arrival counts against the
+// barrier's expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
