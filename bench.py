@@ -492,8 +492,8 @@ def measure_partition(cfg_id, device, rank, world, steps, warmup, math="auto", b
     out = {"workload": c["workload"], "batch": B, "n_gpus": world, "scaling": "strong",
            "value": B * steps / (dev_ms * 1e-3), "unit": "forecast-steps/s", "ms_per_step": dev_ms / steps,
            "e2e": {"value": B * steps / (e2e_ms * 1e-3), "unit": "forecast-steps/s",
-                   "h2d_bytes_per_step": B * ds.num_grid_nodes * (D_FORCING + D_STATE) * 4,
-                   "d2h_bytes_per_step": B * ds.num_grid_nodes * D_STATE * 4},
+                   "h2d_bytes_per_step": fc.host_io_bytes_per_step(B)[0],
+                   "d2h_bytes_per_step": fc.host_io_bytes_per_step(B)[1]},
            "parallelism": ("single GPU, whole graph" if world == 1 else
                            f"node partition x{world}: grid + every mesh level in {world} strips, halo rows pushed into the "
                            "peers' symmetric-memory buffers by halo_push_kernel over NVLink, one device barrier per "
@@ -651,8 +651,7 @@ def run_ours(args):
             cpu = {"value": v, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
                    "sample": f"B={B} (same batch as the GPU arm), {n_cpu} AR steps of the same GraphLAM config after 1 "
                              f"warm-up ({sec:.3f} s per step of {B} forecasts, torch CPU {torch.get_num_threads()} threads)"}
-        h2d = B * G * (D_FORCING + D_STATE) * 4
-        d2h = B * G * D_STATE * 4
+        h2d, d2h = fc.host_io_bytes_per_step(B)  # forcing + the boundary-mask rows of the boundary state in, prediction out
         line = {
             "metric": METRIC,
             "value": world * B * K / (dev_ms * 1e-3),

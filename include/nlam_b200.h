@@ -245,6 +245,11 @@ int nlam_add_gather(const float* a, const float* v, const int32_t* idx, const in
 int nlam_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
                         int host_to_device, void* stream);
 
+/* The same with a depth: `depth` slices of `height` rows; slice stride = pitch * rows-per-slice on either side
+ * (cudaMemcpy3DAsync).  Used to move only the boundary frame of a forecast step's boundary tensor. */
+int nlam_memcpy3d_async(void* dst, size_t dpitch, size_t drows, const void* src, size_t spitch, size_t srows, size_t width_bytes,
+                        size_t height, size_t depth, int host_to_device, void* stream);
+
 /* new_state = bmask * boundary + (1-bmask) * (prev + net_out*diff_std + diff_mean)
  * over (B,G,D); bmask (G), diff_std/mean (D); boundary may be NULL (then bmask ignored). */
 int nlam_step_epilogue(const float* net_out, const float* prev, const float* boundary,

@@ -551,6 +551,23 @@ extern "C" int nlam_halo_push(const float* own, int64_t own_bs, int64_t n_own, f
 
 // One strided host<->device copy per tensor and forecast step (ARForecaster.rollout_from_host): the step-i slice of a
 // (B, T, G, F) host tensor is B rows of G*F floats with pitch T*G*F — one cudaMemcpy2DAsync instead of B small copies.
+// depth x height rows of width_bytes; row pitch and rows-per-slice (slice stride = pitch * rows) on either side: the
+// boundary frame of a forecast step (the strips left and right of the interior: runs of nodes one grid row apart,
+// for every sample) in ONE cudaMemcpy3DAsync
+extern "C" int nlam_memcpy3d_async(void* dst, size_t dpitch, size_t drows, const void* src, size_t spitch, size_t srows,
+                                   size_t width_bytes, size_t height, size_t depth, int host_to_device, void* stream) {
+  NLAM_REQUIRE(dst && src && height <= drows && height <= srows && width_bytes <= dpitch && width_bytes <= spitch,
+               NLAM_E_INVALID, "memcpy3d: bad arguments");
+  cudaMemcpy3DParms q;
+  memset(&q, 0, sizeof(q));
+  q.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), spitch, spitch, srows);
+  q.dstPtr = make_cudaPitchedPtr(dst, dpitch, dpitch, drows);
+  q.extent = make_cudaExtent(width_bytes, height, depth);
+  q.kind = host_to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  NLAM_CUDA_OK(cudaMemcpy3DAsync(&q, (cudaStream_t)stream));
+  return NLAM_OK;
+}
+
 extern "C" int nlam_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes,
                                    size_t height, int host_to_device, void* stream) {
   NLAM_REQUIRE(dst && src, NLAM_E_INVALID, "memcpy2d: null pointer");

@@ -470,6 +470,39 @@ class HiLAMParallel(BaseHiGraphModel):
 MODELS = {"graph_lam": GraphLAM, "hi_lam": HiLAM, "hi_lam_parallel": HiLAMParallel}
 
 
+def _boundary_blocks(mask, max_blocks=8, min_saving=0.2):
+    """Row runs of a (G,) boundary mask as copy blocks ``(start node, run length, pitch, count)``: ``count`` runs of
+    ``run length`` nodes, ``pitch`` nodes apart (count == 1: a single run).  None when the mask is not worth compacting
+    (everything selected, too fragmented for a handful of strided copies, or the strips do not tile the grid evenly)."""
+    m = (mask.reshape(-1) > 0).to("cpu").numpy().astype("int8")
+    G = m.shape[0]
+    if G == 0 or m.sum() == 0 or m.sum() > (1.0 - min_saving) * G:
+        return None
+    import numpy as np
+    d = np.diff(np.concatenate([[0], m, [0]]))
+    starts, ends = np.nonzero(d == 1)[0], np.nonzero(d == -1)[0]
+    runs = list(zip(starts.tolist(), (ends - starts).tolist()))
+    blocks, j = [], 0
+    while j < len(runs):
+        s0, l0 = runs[j]
+        n = 1
+        if j + 1 < len(runs) and runs[j + 1][1] == l0:
+            pitch = runs[j + 1][0] - s0
+            while j + n < len(runs) and runs[j + n][1] == l0 and runs[j + n][0] == s0 + n * pitch:
+                n += 1
+            # a 3-D copy needs the slice stride (G nodes per sample) to be a whole number of pitches
+            if n > 1 and (G % pitch != 0 or l0 > pitch or n > G // pitch or l0 < 4):  # (runs of a few bytes: not worth it)
+                n = 1
+        if n > 1:
+            blocks.append((s0, l0, pitch, n))
+        else:
+            blocks.append((s0, l0, 0, 1))
+        j += n
+        if len(blocks) > max_blocks:
+            return None
+    return blocks
+
+
 class ARForecaster(nn.Module):
     """Autoregressive rollout with boundary overwrite (reference
     models/forecasters/autoregressive.py:63-149).  ``forward`` keeps the reference semantics;
@@ -581,6 +614,16 @@ class ARForecaster(nn.Module):
         return out
 
     @torch.no_grad()
+    def host_io_bytes_per_step(self, B):
+        """(host->device, device->host) bytes ``rollout_from_host`` moves per AR step of B forecasts: the forcing, the rows of
+        the boundary state the boundary mask selects, and the prediction."""
+        self._ensure_captured(B)
+        _, _, bufs = self._graph
+        G, d_state = bufs["boundary"].shape[1], bufs["boundary"].shape[2]
+        blocks = _boundary_blocks(self.boundary_mask)
+        bnd_rows = G if blocks is None else sum(rlen * count for _, rlen, _, count in blocks)
+        return B * (G * bufs["forcing"].shape[2] + bnd_rows * d_state) * 4, B * G * d_state * 4
+
     def rollout_from_host(self, init_states, forcing_features, boundary_states, out=None):
         """Inference rollout with HOST tensors (ideally pinned).  Every AR step copies that step's
         forcing + boundary states host->device, replays the captured step graph and copies the
@@ -598,8 +641,11 @@ class ARForecaster(nn.Module):
             self._io = {
                 "B": B, "s_in": torch.cuda.Stream(device=dev), "s_out": torch.cuda.Stream(device=dev),
                 "forc": [torch.empty_like(bufs["forcing"]) for _ in range(2)],
-                "bnd": [torch.empty_like(bufs["boundary"]) for _ in range(2)],
+                # zero-filled: with a compact boundary transfer the interior rows are never written (and multiplied by a
+                # zero mask in the step epilogue)
+                "bnd": [torch.zeros_like(bufs["boundary"]) for _ in range(2)],
                 "out": [torch.empty_like(bufs["boundary"]) for _ in range(2)],
+                "bnd_blocks": _boundary_blocks(self.boundary_mask),
             }
         io = self._io
         main = torch.cuda.current_stream(dev)
@@ -618,8 +664,28 @@ class ARForecaster(nn.Module):
             args = (dev_t.data_ptr(), row, hp, host_t.stride(0) * 4) if to_device else (hp, host_t.stride(0) * 4, dev_t.data_ptr(), row)
             _lib.check(_lib.lib().nlam_memcpy2d_async(*args, row, B, 1 if to_device else 0, ctypes.c_void_p(stream.cuda_stream)))
 
-        dense = all(t.is_contiguous() and t.dtype == torch.float32 and not t.is_cuda
-                    for t in (forcing_features, boundary_states, init_states, out))
+        def sliceable(t):  # (B, T, G, F) with dense (G, F) blocks, steps G*F apart: slices along T of a dense tensor qualify
+            return (t.dtype == torch.float32 and not t.is_cuda and t.dim() == 4 and t.stride(3) == 1
+                    and t.stride(2) == t.shape[3] and t.stride(1) == t.shape[2] * t.shape[3]
+                    and t.stride(0) % (t.shape[2] * t.shape[3]) == 0)
+
+        dense = all(sliceable(t) for t in (forcing_features, boundary_states, out))
+
+        def copy_boundary(dev_t, host_t, i, stream):
+            """only the rows the boundary mask selects (new = mask*boundary + (1-mask)*prediction never reads the others):
+            the blocks of ``_boundary_blocks`` — a run of nodes per sample, or equally spaced runs (the strips left and
+            right of the interior) as one 3-D copy"""
+            Bh, Th, G, F = host_t.shape
+            L = _lib.lib()
+            sp = ctypes.c_void_p(stream.cuda_stream)
+            for start, rlen, pitch, count in io["bnd_blocks"]:
+                hp = host_t.data_ptr() + (i * G + start) * F * 4
+                dp = dev_t.data_ptr() + start * F * 4
+                if count == 1:
+                    _lib.check(L.nlam_memcpy2d_async(dp, G * F * 4, hp, host_t.stride(0) * 4, rlen * F * 4, Bh, 1, sp))
+                else:
+                    _lib.check(L.nlam_memcpy3d_async(dp, pitch * F * 4, G // pitch, hp, pitch * F * 4,
+                                                     host_t.stride(0) // (pitch * F), rlen * F * 4, count, Bh, 1, sp))
 
         def h2d(i):
             k = i & 1
@@ -628,7 +694,10 @@ class ARForecaster(nn.Module):
                     s_in.wait_event(in_free[k])
                 if dense:
                     copy_step(io["forc"][k], forcing_features, i, s_in, True)
-                    copy_step(io["bnd"][k], boundary_states, i, s_in, True)
+                    if io["bnd_blocks"] is not None:
+                        copy_boundary(io["bnd"][k], boundary_states, i, s_in)
+                    else:
+                        copy_step(io["bnd"][k], boundary_states, i, s_in, True)
                 else:
                     for b in range(B):  # per-sample slices of (B,T,G,F) host tensors are contiguous
                         io["forc"][k][b].copy_(forcing_features[b, i], non_blocking=True)

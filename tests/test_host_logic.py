@@ -126,3 +126,29 @@ def test_graph_csr_cache_roundtrip(tmp_path, hier):
     torch.save(raw["g2m_features"][:-1], os.path.join(d, "g2m_features.pt"))
     stale = synthetic.load_graph(d, spec["grid_xy"])
     assert torch.equal(stale["g2m_edge_index"], raw["g2m_edge_index"][:, :-1])
+
+
+def test_boundary_blocks_cover_exactly_the_masked_rows():
+    """rollout_from_host moves only the boundary-mask rows of the boundary state: a frame mask becomes two runs (top, bottom) and
+    one block of equally spaced runs (the strips left and right of the interior)."""
+    import numpy as np
+    from neural_lam_b200.models import _boundary_blocks
+
+    for nx, ny, w in ((268, 238, 10), (30, 27, 2), (16, 16, 2)):
+        m = torch.zeros(nx, ny)
+        m[:w] = 1
+        m[-w:] = 1
+        m[:, :w] = 1
+        m[:, -w:] = 1
+        blocks = _boundary_blocks(m.reshape(-1, 1))
+        assert blocks is not None and len(blocks) == 3
+        hit = np.zeros(nx * ny)
+        for start, rlen, pitch, count in blocks:
+            for j in range(count):
+                hit[start + j * pitch:start + j * pitch + rlen] += 1
+            if count > 1:
+                assert (nx * ny) % pitch == 0 and rlen <= pitch
+        assert (hit == m.reshape(-1).numpy()).all()
+    assert _boundary_blocks(torch.ones(64, 1)) is None                      # nothing to save
+    assert _boundary_blocks(torch.zeros(64, 1)) is None
+    assert _boundary_blocks((torch.arange(4000) % 3 == 0).float().reshape(-1, 1)) is None  # too fragmented

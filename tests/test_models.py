@@ -115,6 +115,12 @@ def test_step_and_rollout_match_oracle_fp32(kind):
         ref5 = fc.rollout_graphed(init.cuda(), forc5.cuda(), bnd5.cuda())
     assert not host.is_cuda
     torch.testing.assert_close(host, ref5.cpu(), rtol=0, atol=0)
+    # slices along T of pinned tensors take the same strided-copy path (one copy per tensor and step, boundary rows only)
+    out3 = torch.empty(B, T5, G, 5).pin_memory()
+    with torch.no_grad():
+        fc.rollout_from_host(init.pin_memory(), forc5[:, 2:], bnd5[:, 2:], out=out3[:, :3])
+        ref3 = fc.rollout_graphed(init.cuda(), forc5[:, 2:].cuda(), bnd5[:, 2:].cuda())
+    torch.testing.assert_close(out3[:, :3], ref3.cpu(), rtol=0, atol=0)
     err64 = (got.cpu().double() - want64).abs().max().item()
     ref64 = (want.double() - want64).abs().max().item()
     assert err64 < max(10 * ref64, 2e-4), (err64, ref64)
