@@ -237,20 +237,32 @@ def roofline_m2m(model, B, device, iters=20):
     edge = torch.randn(B, E, H, generator=g).to(device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    # as the forecast step runs the middle layers of the processor stack: e' written over e (same bytes moved as the
+    # out-of-place call: E rows read, E rows written); the stand-alone out-of-place call is timed next to it
+    stacked = hasattr(layer, "forward_stacked")
+
+    def call(inplace):
+        if inplace and stacked:
+            layer.forward_stacked(mesh, edge, first=False, last=False)
+        else:
+            layer(mesh, mesh, edge)
+
+    res = {}
     with torch.no_grad():
-        for _ in range(3):
-            layer(mesh, mesh, edge)
-        torch.cuda.synchronize(device)
-        for s, e in ev:
-            flush.zero_()
-            s.record()
-            layer(mesh, mesh, edge)
-            e.record()
-        torch.cuda.synchronize(device)
-    ms = sorted(s.elapsed_time(e) for s, e in ev)
-    mean_ms = sum(ms) / len(ms)
+        for inplace in (False, True):
+            for _ in range(3):
+                call(inplace)
+            torch.cuda.synchronize(device)
+            for s, e in ev:
+                flush.zero_()
+                s.record()
+                call(inplace)
+                e.record()
+            torch.cuda.synchronize(device)
+            ms = sorted(s.elapsed_time(e) for s, e in ev)
+            res[inplace] = (sum(ms) / len(ms), ms[len(ms) // 2])
     nbytes = algorithmic_bytes_inet(B, Nm, Nm, E, H, True, True)
-    return nbytes, mean_ms, ms[len(ms) // 2]
+    return nbytes, res[True][0], res[True][1], res[False][0]
 
 
 
@@ -613,7 +625,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = _peaks()
         with torch.no_grad():
-            nbytes, mean_ms, med_ms = roofline_m2m(model, B, device)
+            nbytes, mean_ms, med_ms, oop_ms = roofline_m2m(model, B, device)
         achieved = nbytes / (mean_ms * 1e-3) / 1e9
         # DRAM traffic of the roofline kernel from an `ncu --set full` capture AT THIS BATCH (profiles/traffic.json:
         # {"m2m_layer_dram_bytes": {"<B>": bytes}}); null when no capture exists for the batch that was run
@@ -621,7 +633,7 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             try:
-                traffic = json.load(open(tp)).get("m2m_layer_dram_bytes", {}).get(str(B))
+                traffic = json.load(open(tp)).get("m2m_layer_inplace_dram_bytes", {}).get(str(B))
             except Exception:
                 traffic = None
         sb, sf = step_algorithmic(model, B)
@@ -672,7 +684,9 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step) * K,
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "m2m InteractionNet layer (nlam_inet_fwd, all launches)",
+            "roofline": {"bound": "hbm", "kernel": "m2m InteractionNet layer as the step runs its middle layers (nlam_inet_fwd, "
+                                                   "edge tensor updated in place; all 3 launches)",
+                         "out_of_place_ms": oop_ms,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": nbytes, "ms_mean": mean_ms, "ms_median": med_ms,
                          "peak_source": peak_src, "l2_flushed": True},

@@ -57,6 +57,8 @@ extern "C" {
 #define NLAM_MATH_TF32 0x10       /* tcgen05 TF32 tensor-core kernels (fp32 accumulate) */
 #define NLAM_MATH_FP32 0x20       /* exact fp32 FFMA kernels */
 #define NLAM_HINT_ONE_HIDDEN 0x100 /* promise to nlam_inet_workspace_bytes: both MLPs are Linear-SiLU-Linear-LayerNorm */
+#define NLAM_EDGE_ONLY 0x200      /* nlam_inet_fwd: stop after the aggregation (aggr_out required; rec_out unused): the node
+                                     update runs in a later call, e.g. nlam_node_update_step_fwd */
 /* neither math flag: TF32 when the shape is supported by the tensor-core kernels, else FP32 */
 
 #define NLAM_MAX_LINEAR 4
@@ -156,6 +158,16 @@ int nlam_inet_inplace_supported(const NlamGraph* g, const NlamMlp* edge_mlp, con
 int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res,
                     const NlamRowSrc* res2, float* out, float* out2, int64_t n_rows, int B,
                     int flags, void* stream);
+
+/* Tail of the grid side of a forecast step in one launch (csrc/tc9.cu): the node update of the mesh->grid InteractionNet
+ *   grid' = rec + node_mlp([rec | aggr])              (reference gnn_layers.py:148-151)
+ * chained with output_map and the step epilogue of nlam_rowmlp_step_fwd; grid' never leaves the SM.  rec (B, n_rows, 64)
+ * with batch stride rec_bstride, aggr (B, n_rows, 64) dense (nlam_inet_fwd with NLAM_EDGE_ONLY).  NLAM_E_UNSUPPORTED for
+ * shapes / math modes the fused kernel does not cover (callers then run nlam_inet_fwd + nlam_rowmlp_step_fwd). */
+int nlam_node_update_step_fwd(const NlamMlp* node_mlp, const NlamMlp* out_mlp, const float* rec, int64_t rec_bstride,
+                              const float* aggr, const float* prev, const float* boundary, const float* bmask,
+                              const float* diff_std, const float* diff_mean, float* new_state, int64_t n_rows, int B,
+                              int flags, void* stream);
 
 /* out[b,n,:] = scale_n * sum_{k in [ptr[n],ptr[n+1])} x[b, order ? order[k] : k, :]
  * scale_n = 1 (sum) or 1/max(deg,1) (mean).  Deterministic, CSR order. */

@@ -18,6 +18,7 @@ PROPAGATION = 0x2
 MATH_TF32 = 0x10
 MATH_FP32 = 0x20
 HINT_ONE_HIDDEN = 0x100
+EDGE_ONLY = 0x200
 E_UNSUPPORTED = 2  # NLAM_E_UNSUPPORTED
 
 c_float_p = ctypes.c_void_p  # device pointers travel as integers
@@ -141,6 +142,10 @@ SYMBOLS = {
     "nlam_add_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "nlam_memcpy2d_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                             ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "nlam_node_update_step_fwd": (ctypes.c_int, [
+        ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamMlp), ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p]),
     "nlam_memcpy3d_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                             ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                             ctypes.c_void_p]),

@@ -51,6 +51,19 @@ extern "C" int nlam_rowmlp_step_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, 
   return tc_rowmlp(mlp, srcs, n_src, nullptr, new_state, n_rows, B, (cudaStream_t)stream, &ep);
 }
 
+extern "C" int nlam_node_update_step_fwd(const NlamMlp* node_mlp, const NlamMlp* out_mlp, const float* rec, int64_t rec_bs,
+                                         const float* aggr, const float* prev, const float* boundary, const float* bmask,
+                                         const float* diff_std, const float* diff_mean, float* new_state, int64_t n_rows, int B,
+                                         int flags, void* stream) {
+  NLAM_REQUIRE(node_mlp && out_mlp && rec && aggr && prev && diff_std && diff_mean && new_state, NLAM_E_INVALID,
+               "nlam_node_update_step_fwd: null argument");
+  NLAM_REQUIRE((boundary == nullptr) || bmask, NLAM_E_INVALID, "nlam_node_update_step_fwd: boundary without mask");
+  StepEpilogue ep = {prev, boundary, bmask, diff_std, diff_mean};
+  NLAM_REQUIRE(want_tf32(flags) && tc_node_out_supported(node_mlp, out_mlp, rec, rec_bs, aggr, n_rows, B, new_state, &ep),
+               NLAM_E_UNSUPPORTED, "nlam_node_update_step_fwd: shape / math mode not covered by the fused kernel");
+  return tc_node_out(node_mlp, out_mlp, rec, rec_bs, aggr, n_rows, B, new_state, &ep, (cudaStream_t)stream);
+}
+
 static size_t rup256(size_t n) { return (n + 255) / 256 * 256; }
 
 // Workspace layout: [aggregate | path-specific scratch].  Sized per path: the fused H = 64 kernels need only the node
@@ -100,7 +113,10 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
                              const float* edge, int64_t edge_bs, float* rec_out, float* edge_out,
                              float* aggr_out, int B, int flags, void* workspace, size_t ws_bytes,
                              void* stream) {
-  NLAM_REQUIRE(g && edge_mlp && aggr_mlp && send && rec && edge && rec_out, NLAM_E_INVALID, "nlam_inet_fwd: null argument");
+  const bool edge_only = flags & NLAM_EDGE_ONLY;
+  NLAM_REQUIRE(g && edge_mlp && aggr_mlp && send && rec && edge && (rec_out || edge_only), NLAM_E_INVALID,
+               "nlam_inet_fwd: null argument");
+  NLAM_REQUIRE(!edge_only || aggr_out, NLAM_E_INVALID, "nlam_inet_fwd: NLAM_EDGE_ONLY needs aggr_out");
   NLAM_REQUIRE(B >= 1, NLAM_E_INVALID, "nlam_inet_fwd: bad batch");
   const int H = edge_mlp->out_dim[edge_mlp->n_linear - 1];
   NLAM_REQUIRE(edge_mlp->in_dim == 3 * H && aggr_mlp->in_dim == 2 * H &&
@@ -127,6 +143,7 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   NLAM_REQUIRE(use_tc || use_gen || !(flags & NLAM_MATH_TF32), NLAM_E_UNSUPPORTED,
                "nlam_inet_fwd: shape (H=%d, max in-degree %d, hidden_layers=%d) not supported by the tcgen05 kernels",
                H, g->max_in_degree, edge_mlp->n_linear - 1);
+  NLAM_REQUIRE(!(use_gen && edge_only), NLAM_E_UNSUPPORTED, "nlam_inet_fwd: NLAM_EDGE_ONLY is not available on the generic path");
   if (use_gen)
     return tc_inet_gen(g, edge_mlp, aggr_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, rec_out, edge_out, aggr, B, flags,
                        scratch, st);
@@ -164,6 +181,7 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
     rc = nlam_segment_sum(g->rowptr, nullptr, g->n_rec, msg, (int64_t)g->n_edges * H, aggr, aggr_bs, B, H, mean, st);
     if (rc) return rc;
   }
+  if (edge_only) return NLAM_OK;
   // node update: rec' = base + aggr_mlp(cat(rec, aggr)); base = rec (InteractionNet) or aggr (PropagationNet)
   NlamRowSrc nsrcs[2] = {{rec, nullptr, rec_bs, H, 0}, {aggr, nullptr, aggr_bs, H, 0}};
   NlamRowSrc nres = prop ? nsrcs[1] : nsrcs[0];

@@ -350,6 +350,23 @@ class InteractionNet(nn.Module):
                                             edge_inplace=inplace)
         return rec_out, edge_out
 
+    @torch.no_grad()
+    def aggregate_only(self, send_rep, rec_rep, edge_rep):
+        """Inference-only: the edge stage of the layer (messages + aggregation) WITHOUT the node update; returns the (B, Nr, H)
+        aggregate, or None when this layer / call shape has no such kernel path (the caller then runs ``forward``).  Used to
+        chain the node update of the mesh->grid layer with the output MLP in one kernel (``ops.node_update_step``)."""
+        if (self._halo is not None or self.update_edges or self.propagation or not self._fusable() or not self._is_sorted
+                or self.edge_mlp[0].in_features != 192):
+            return None
+        self._check_inputs(send_rep, rec_rep, edge_rep)
+        _, (s3, r3, e3) = self._batchify(send_rep, rec_rep, edge_rep)
+        try:
+            _, _, aggr = ops.inet_fwd(self._graph(r3.device), self.edge_mlp, self.aggr_mlp, s3, r3, e3, False, self._flags(),
+                                      edge_only=True)
+        except _lib.NlamError:
+            return None
+        return aggr
+
     def propagate(self, edge_index, x=None, edge_attr=None, size=None):
         """PyG-style entry kept for API compatibility (reference tests call it directly,
         tests/test_gnn_layers.py:249,:290,:380): ``x`` is ``cat(rec_rep, send_rep)`` along the

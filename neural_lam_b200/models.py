@@ -250,8 +250,23 @@ class BaseGraphModel(StepPredictor):
         mesh_rep = self.g2m_gnn(grid_emb, self.expand_to_batch(st["mesh_emb"], B), self.expand_to_batch(st["g2m_emb"], B))
         grid_rep = self.encoding_grid_mlp.apply_rows([grid_emb], res=grid_emb)
         mesh_rep = self.process_step(mesh_rep, st)
-        grid_rep = self.m2g_gnn(mesh_rep, grid_rep, self.expand_to_batch(st["m2g_emb"], B))
         clamp = (self._clamp_kind, self._clamp_lo, self._clamp_up) if self.clamps_output else None
+        m2g_emb = self.expand_to_batch(st["m2g_emb"], B)
+        if clamp is None and hasattr(self.m2g_gnn, "aggregate_only"):
+            # node update of the mesh->grid layer + output_map + step epilogue in one kernel: the updated grid
+            # representation (which nothing else reads) never goes to HBM
+            aggr = self.m2g_gnn.aggregate_only(mesh_rep, grid_rep, m2g_emb)
+            if aggr is not None:
+                fused = ops.node_update_step(self.m2g_gnn.aggr_mlp, self.output_map, grid_rep, aggr, prev_state, boundary_state,
+                                             boundary_mask, self.diff_std, self.diff_mean,
+                                             flags=self.output_map.nlam_flags, out=out)
+                if fused is not None:
+                    return fused
+                grid_rep = self.m2g_gnn._kernel_node_update(grid_rep, aggr)
+            else:
+                grid_rep = self.m2g_gnn(mesh_rep, grid_rep, m2g_emb)
+        else:
+            grid_rep = self.m2g_gnn(mesh_rep, grid_rep, m2g_emb)
         if clamp is None:
             fused = ops.rowmlp_step(self.output_map, grid_rep, prev_state, boundary_state, boundary_mask, self.diff_std,
                                     self.diff_mean, flags=self.output_map.nlam_flags, out=out)

@@ -291,10 +291,12 @@ class SegmentSumFn(torch.autograd.Function):
         return gm, None, None, None, None
 
 
-def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags, want_aggr=False, edge_inplace=False):
+def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags, want_aggr=False, edge_inplace=False,
+             edge_only=False):
     """One fused InteractionNet/PropagationNet forward through ``nlam_inet_fwd``.
     ``edge_csr`` must be in CSR edge order.  ``edge_inplace``: write e' = e + m over ``edge_csr`` itself (a dense
-    batched tensor the caller owns).  Returns (rec_out, edge_out|None, aggr|None), 3-D."""
+    batched tensor the caller owns).  ``edge_only``: stop after the aggregation (``NLAM_EDGE_ONLY``; the node update runs in a
+    later call, see ``node_update_step``); rec_out is None then.  Returns (rec_out, edge_out|None, aggr|None), 3-D."""
     L = _lib.lib()
     s, Bs, sbs = as_rows(send)
     r, Br, rbs = as_rows(rec)
@@ -316,7 +318,8 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
         raise RuntimeError(f"graph handle lives on {graph.device}, tensors on {dev}")
     em = mlp_struct(edge_seq)
     am = mlp_struct(aggr_seq)
-    rec_out = torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32)
+    want_aggr = want_aggr or edge_only
+    rec_out = None if edge_only else torch.empty((B, graph.n_rec, H), device=dev, dtype=torch.float32)
     if (update_edges and edge_inplace and Be == B and (B == 1 or ebs == graph.n_edges * H)
             and L.nlam_inet_inplace_supported(graph.handle, ctypes.byref(em), s.data_ptr(), sbs, r.data_ptr(), rbs,
                                               e.data_ptr(), ebs, B, flags)):
@@ -331,8 +334,8 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
         _lib.check(L.nlam_inet_fwd(
             graph.handle, ctypes.byref(em), ctypes.byref(am),
             s.data_ptr(), sbs, r.data_ptr(), rbs, e.data_ptr(), ebs,
-            rec_out.data_ptr(), edge_out.data_ptr() if update_edges else None,
-            aggr.data_ptr() if want_aggr else None, B, flags,
+            rec_out.data_ptr() if rec_out is not None else None, edge_out.data_ptr() if update_edges else None,
+            aggr.data_ptr() if want_aggr else None, B, flags | (_lib.EDGE_ONLY if edge_only else 0),
             ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
     return rec_out, edge_out, aggr
 
@@ -401,6 +404,41 @@ def rowmlp_step(seq, x, prev, boundary, bmask, diff_std, diff_mean, flags=0, out
                                     bmask.data_ptr() if boundary is not None else None,
                                     diff_std.data_ptr(), diff_mean.data_ptr(), out.data_ptr(), G, B, flags,
                                     _stream_ptr(xr.device))
+    if rc == _lib.E_UNSUPPORTED:
+        return None
+    _lib.check(rc)
+    return out
+
+
+def node_update_step(node_seq, out_seq, rec, aggr, prev, boundary, bmask, diff_std, diff_mean, flags=0, out=None):
+    """``bmask*boundary + (1-bmask)*(prev + out_seq(rec + node_seq([rec | aggr]))*diff_std + diff_mean)`` in ONE launch
+    (``nlam_node_update_step_fwd``: node update of the mesh->grid layer + output_map + forecast-step epilogue; the updated
+    grid representation never goes to HBM).  Returns None when the library does not fuse this shape / math mode."""
+    L = _lib.lib()
+    if flags & _lib.MATH_FP32:
+        return None
+    rr, B, rbs = as_rows(rec)
+    ar, Ba, abs_ = as_rows(aggr)
+    prev = prev.contiguous()
+    _require_cuda(rr, ar, prev, diff_std, diff_mean, boundary, bmask)
+    nm, om = mlp_struct(node_seq), mlp_struct(out_seq)
+    D = om.out_dim[om.n_linear - 1]
+    G = rr.shape[-2]
+    Bt = max(B, Ba)
+    if (rr.shape[-1] != 64 or ar.shape[-1] != 64 or ar.shape[-2] != G or D >= 64 or om.ln_gamma or prev.shape != (Bt, G, D)
+            or Ba != Bt or (Bt > 1 and abs_ != G * 64) or B not in (1, Bt)):
+        return None
+    if boundary is not None:
+        boundary, bmask = boundary.contiguous(), bmask.contiguous()
+        assert boundary.shape == prev.shape and bmask.numel() == G
+    if out is None:
+        out = torch.empty_like(prev)
+    assert out.is_contiguous() and out.shape == prev.shape and out.data_ptr() != prev.data_ptr()
+    with torch.cuda.device(rr.device):
+        rc = L.nlam_node_update_step_fwd(ctypes.byref(nm), ctypes.byref(om), rr.data_ptr(), rbs if B > 1 else 0, ar.data_ptr(),
+                                         prev.data_ptr(), boundary.data_ptr() if boundary is not None else None,
+                                         bmask.data_ptr() if boundary is not None else None, diff_std.data_ptr(),
+                                         diff_mean.data_ptr(), out.data_ptr(), G, Bt, flags, _stream_ptr(rr.device))
     if rc == _lib.E_UNSUPPORTED:
         return None
     _lib.check(rc)

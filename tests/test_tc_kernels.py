@@ -521,3 +521,47 @@ def test_stack_updates_private_edge_tensor_in_place():
     assert prof.names().count("tc_edge_rmw_kernel") == 3 and prof.names().count("tc_edge3_kernel") == 1, prof.names()
     assert torch.equal(e_static, keep)
     assert (got - want).abs().max().item() <= 5e-3
+
+
+@pytest.mark.parametrize("with_boundary,B,G", [(True, 3, 1000), (False, 1, 128), (True, 2, 40 * 128 + 36)])
+def test_chained_node_update_output_map_step_epilogue(with_boundary, B, G):
+    """tc9.cu: node update of the mesh->grid layer + output_map + forecast-step epilogue in one launch, against the
+    two-kernel path (tc4.cu node update, then output_map + epilogue) on the same inputs: same TF32 products, same fp32
+    formulas — the intermediate only stays in shared memory."""
+    from neural_lam_b200.networks import make_mlp
+    torch.manual_seed(3)
+    ei = _graph(50, G, 4 * G, 2, True)
+    net = nlb.InteractionNet(ei, 64, update_edges=False, math="tf32").to(DEV)
+    out_map = make_mlp([64, 64, 17], layer_norm=False).to(DEV)
+    with torch.no_grad():
+        for p in list(net.parameters()) + list(out_map.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    rec = torch.randn(B, G, 64, device=DEV)
+    aggr = torch.randn(B, G, 64, device=DEV)
+    prev = torch.randn(B, G, 17, device=DEV)
+    bnd = torch.randn(B, G, 17, device=DEV) if with_boundary else None
+    mask = (torch.rand(G, 1, device=DEV) < 0.3).float() if with_boundary else None
+    std, mean = torch.rand(17, device=DEV) + 0.5, torch.randn(17, device=DEV)
+    with torch.no_grad():
+        with ops.profile_launches() as prof:
+            got = ops.node_update_step(net.aggr_mlp, out_map, rec, aggr, prev, bnd, mask, std, mean)
+        assert got is not None and prof.names() == ["tc_node_out_kernel"], prof.names()
+        grid2 = net._kernel_node_update(rec, aggr)
+        want = ops.rowmlp_step(out_map, grid2, prev, bnd, mask, std, mean)
+        assert want is not None
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    # and against plain torch in fp64 (TF32 tolerance)
+    sd = {k: v.double().cpu() for k, v in net.state_dict().items()}
+    x = torch.cat([rec, aggr], -1).double().cpu()
+    h = torch.nn.functional.silu(x @ sd["aggr_mlp.0.weight"].T + sd["aggr_mlp.0.bias"])
+    y = torch.nn.functional.layer_norm(h @ sd["aggr_mlp.2.weight"].T + sd["aggr_mlp.2.bias"], (64,),
+                                       sd["aggr_mlp.3.weight"], sd["aggr_mlp.3.bias"])
+    g2 = rec.double().cpu() + y
+    od = {k: v.double().cpu() for k, v in out_map.state_dict().items()}
+    o = torch.nn.functional.silu(g2 @ od["0.weight"].T + od["0.bias"]) @ od["2.weight"].T + od["2.bias"]
+    new = prev.double().cpu() + o * std.double().cpu() + mean.double().cpu()
+    if with_boundary:
+        m = mask.double().cpu()
+        new = m * bnd.double().cpu() + (1 - m) * new
+    assert (got.double().cpu() - new).abs().max().item() < 2e-2
