@@ -98,6 +98,7 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
   const uint32_t bar_staged = mb + 272;     // [3] result slab written (256 arrivals)
   const uint32_t bar_ep_full = mb + 296;    // [3] prev / boundary / mask slabs landed (tx bytes)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 320);
+  volatile int* sel = reinterpret_cast<volatile int*>(smem + OFF_MISC + 328);  // [2 groups][2]: which stage a group runs next
   float* sprm = reinterpret_cast<float*>(smem + OFF_MISC + 512);  // gamma | beta | b1/2 | b3/2 | std | mean | b4 (64 each)
   float* s_gamma = sprm, *s_beta = sprm + 64, *s_b1h = sprm + 128, *s_b3h = sprm + 192, *s_std = sprm + 256,
         *s_mean = sprm + 320, *s_b4 = sprm + 384;
@@ -180,6 +181,16 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
         mbar_expect_tx(bar_g_full, 2u * BLK);
         tma_load_3d(sbase + OFF_G, &tmG, bar_g_full, 0, t * 128, b, pol_stream);
         tma_load_3d(sbase + OFF_G + BLK, &tmG, bar_g_full, 32, t * 128, b, pol_stream);
+        // pull the tiles after next into L2 (a slot's life starts with its load: 3.4 k cycles from DRAM, measured)
+        for (int a = (ti == 0 ? 1 : 2); a <= 2; ++a) {
+          if (ti + a >= n_my) break;
+          const int w2 = blockIdx.x + (ti + a) * gridDim.x;
+          const int b2 = w2 / p.n_tiles, t2 = w2 - b2 * p.n_tiles;
+          tma_prefetch_3d(&tmR, 0, t2 * 128, p.rec_batched ? b2 : 0);
+          tma_prefetch_3d(&tmR, 32, t2 * 128, p.rec_batched ? b2 : 0);
+          tma_prefetch_3d(&tmG, 0, t2 * 128, b2);
+          tma_prefetch_3d(&tmG, 32, t2 * 128, b2);
+        }
       }
     }
   } else if (warp == W_ST) {
@@ -361,40 +372,57 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
       tc_fence_before();
       mbar_arrive(bar_done + 8 * ts);
     };
+    // Per iteration two stages are pending: the node MLP of tile i and the output MLP of tile i - 1; the group takes
+    // whichever accumulator is ready first (the lead warp polls both barriers and publishes the choice).
+    int round = 0;
     for (int i = 0; i <= n_my; ++i) {
-      if (i < n_my) {  // node MLP of tile i
-        const int ts = i % NT;
-        if (lead) mbar_wait(bar_d1_full + 8 * ts, (uint32_t)((i / NT) & 1));
-        named_bar_sync(1, EPI);
-        tc_fence_after();
-        if (lead && lane == 0) R9_DBG(5, i);
-        silu_stage(ts, s_b1h, bar_hb_full);
-      }
-      if (i >= 1) {  // output MLP of tile i - 1
-        const int ti = i - 1;
-        const int ts = ti % NT;
-        if (lead) mbar_wait(bar_d3_full + 8 * ts, (uint32_t)((ti / NT) & 1));
-        if (lead && lane == 0 && p.ep_prev) {
-          // the third GEMM has consumed grid': the slot takes the prev / boundary / mask slabs of the tile (contiguous in
-          // global memory: one bulk copy each)
-          const int w = blockIdx.x + ti * gridDim.x;
-          const int b = w / p.n_tiles, t = w - b * p.n_tiles;
-          const int nrows = (int)min(128LL, p.n_rows - (long long)t * 128);
-          const uint32_t bytes = (uint32_t)(nrows * p.nout * 4);
-          const uint32_t dst = sbase + OFF_R + (ti % NRS) * 2 * BLK;
-          const long long g0 = ((long long)b * p.n_rows + (long long)t * 128) * p.nout;
-          const uint32_t bar = bar_ep_full + 8 * ts;
-          mbar_expect_tx(bar, p.ep_bnd ? 2u * bytes + (uint32_t)(nrows * 4) : bytes);
-          bulk_load_1d(dst + S_PREV, p.ep_prev + g0, bytes, bar);
-          if (p.ep_bnd) {
-            bulk_load_1d(dst + S_BND, p.ep_bnd + g0, bytes, bar);
-            bulk_load_1d(dst + S_MASK, p.ep_mask + (long long)t * 128, (uint32_t)(nrows * 4), bar);
+      bool pend_a = i < n_my, pend_b = i >= 1;
+      const int ti = i - 1;
+      while (pend_a || pend_b) {
+        if (lead) {
+          int pick = -1;
+          uint32_t spins = 0;
+          while (pick < 0) {
+            if (pend_b && mbar_test_u(bar_d3_full + 8 * (ti % NT), (uint32_t)((ti / NT) & 1))) pick = 1;
+            else if (pend_a && mbar_test_u(bar_d1_full + 8 * (i % NT), (uint32_t)((i / NT) & 1))) pick = 0;
+            else if (__nanosleep(20), ++spins > (1u << 24)) {
+              if (lane == 0) printf("nlam tc_node_out: epilogue group 1 timeout (block %d tile %d)\n", blockIdx.x, i);
+              __trap();
+            }
           }
+          if (lane == 0) sel[round & 1] = pick;
         }
         named_bar_sync(1, EPI);
+        const int pick = sel[round & 1];
+        ++round;
         tc_fence_after();
-        if (lead && lane == 0) R9_DBG(6, ti);
-        silu_stage(ts, s_b3h, bar_hb2_full);
+        if (pick == 0) {  // node MLP of tile i
+          if (lead && lane == 0) R9_DBG(5, i);
+          silu_stage(i % NT, s_b1h, bar_hb_full);
+          pend_a = false;
+        } else {  // output MLP of tile i - 1
+          const int ts = ti % NT;
+          if (lead && lane == 0 && p.ep_prev) {
+            // the third GEMM has consumed grid': the slot takes the prev / boundary / mask slabs of the tile (contiguous
+            // in global memory: one bulk copy each)
+            const int w = blockIdx.x + ti * gridDim.x;
+            const int b = w / p.n_tiles, t = w - b * p.n_tiles;
+            const int nrows = (int)min(128LL, p.n_rows - (long long)t * 128);
+            const uint32_t bytes = (uint32_t)(nrows * p.nout * 4);
+            const uint32_t dst = sbase + OFF_R + (ti % NRS) * 2 * BLK;
+            const long long g0 = ((long long)b * p.n_rows + (long long)t * 128) * p.nout;
+            const uint32_t bar = bar_ep_full + 8 * ts;
+            mbar_expect_tx(bar, p.ep_bnd ? 2u * bytes + (uint32_t)(nrows * 4) : bytes);
+            bulk_load_1d(dst + S_PREV, p.ep_prev + g0, bytes, bar);
+            if (p.ep_bnd) {
+              bulk_load_1d(dst + S_BND, p.ep_bnd + g0, bytes, bar);
+              bulk_load_1d(dst + S_MASK, p.ep_mask + (long long)t * 128, (uint32_t)(nrows * 4), bar);
+            }
+          }
+          if (lead && lane == 0) R9_DBG(6, ti);
+          silu_stage(ts, s_b3h, bar_hb2_full);
+          pend_b = false;
+        }
       }
     }
   } else if (warp < W_E1) {
@@ -411,13 +439,36 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
 #pragma unroll
     for (int i = 0; i < 16; ++i) b2r[i] = make_float2(__ldg(p.b2 + c0 + 2 * i), __ldg(p.b2 + c0 + 2 * i + 1));
     const int nout = p.nout;
+    int round = 0;
     for (int i = 0; i <= n_my; ++i) {
-      if (i < n_my) {
-        // ---- node MLP of tile i: bias, LayerNorm, + grid (residual) -> grid' in place over the grid tile
-        const int ts = i % NT, rs = i % NRS;
-        if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((i / NT) & 1));
+     bool pend_a = i < n_my, pend_b = i >= 1;
+     while (pend_a || pend_b) {
+      {
+        const int tb = i - 1;
+        if (warp == 0) {  // the result epilogue of tile i - 1 first when it is ready: it returns the tile's slot
+          int pick = -1;
+          uint32_t spins = 0;
+          while (pick < 0) {
+            if (pend_b && mbar_test_u(bar_d4_full + 8 * (tb % NT), (uint32_t)((tb / NT) & 1)) &&
+                (!p.ep_prev || mbar_test_u(bar_ep_full + 8 * (tb % NT), (uint32_t)((tb / NT) & 1))))
+              pick = 1;
+            else if (pend_a && mbar_test_u(bar_d2_full + 8 * (i % NT), (uint32_t)((i / NT) & 1))) pick = 0;
+            else if (__nanosleep(20), ++spins > (1u << 24)) {
+              if (lane == 0) printf("nlam tc_node_out: epilogue group 2 timeout (block %d tile %d)\n", blockIdx.x, i);
+              __trap();
+            }
+          }
+          if (lane == 0) sel[2 + (round & 1)] = pick;
+        }
         named_bar_sync(2, EPI);
-        tc_fence_after();
+      }
+      const int pick = sel[2 + (round & 1)];
+      ++round;
+      tc_fence_after();
+      if (pick == 0) {
+        // ---- node MLP of tile i: bias, LayerNorm, + grid (residual) -> grid' in place over the grid tile
+        pend_a = false;
+        const int ts = i % NT, rs = i % NRS;
         if (tid == 0) R9_DBG(7, i);
         float vf[32];
         tmem_ld32(tmem_base + ts * 128 + t_lane + c0, vf);
@@ -458,17 +509,11 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
         fence_proxy_async();  // generic writes -> tcgen05.mma operand reads
         tc_fence_before();
         mbar_arrive(bar_mid + 8 * ts);
-      }
-      if (i >= 1) {
+      } else {
         // ---- output MLP of tile i - 1: this thread finishes columns [9*half, 9*half + 9) of its row
+        pend_b = false;
         const int ti = i - 1;
         const int ts = ti % NT, rs = ti % NRS;
-        if (warp == 0) {
-          mbar_wait(bar_d4_full + 8 * ts, (uint32_t)((ti / NT) & 1));
-          if (p.ep_prev) mbar_wait(bar_ep_full + 8 * ts, (uint32_t)((ti / NT) & 1));
-        }
-        named_bar_sync(2, EPI);
-        tc_fence_after();
         if (tid == 0) R9_DBG(8, ti);
         const float* s_prev = reinterpret_cast<const float*>(smem + OFF_R + rs * 2 * BLK + S_PREV);
         const float* s_bnd = reinterpret_cast<const float*>(smem + OFF_R + rs * 2 * BLK + S_BND);
@@ -497,6 +542,7 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
         fence_proxy_async();
         mbar_arrive(bar_staged + 8 * ts);
       }
+     }
     }
   }
 
