@@ -25,10 +25,10 @@ extern "C" int nlam_rowmlp_fwd(const NlamMlp* mlp, const NlamRowSrc* srcs, int n
     return rc;
   }
   if (want_tf32(flags) && !out2 && tc_mlp2_packed_supported(mlp, srcs, n_src, res, res2)) {
-    // narrow / concatenated inputs at H = 128 / 256: pack, then the two generic Linear launches
+    // narrow / concatenated / gathered inputs (any H of the generic kernel): pack, then the two generic Linear launches
     float* ws = nullptr;
     NLAM_CUDA_OK(cudaMallocAsync((void**)&ws, tc_mlp2_packed_workspace_floats(mlp, n_rows, B) * sizeof(float), st));
-    const int rc = tc_mlp2_packed(mlp, srcs, n_src, out, n_rows, B, st, ws);
+    const int rc = tc_mlp2_packed(mlp, srcs, n_src, res, out, n_rows, B, st, ws);
     NLAM_CUDA_OK(cudaFreeAsync(ws, st));
     return rc;
   }

@@ -110,8 +110,8 @@ int tc_mlp2(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSr
             cudaStream_t st, float* ws);
 bool tc_mlp2_packed_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2);
 size_t tc_mlp2_packed_workspace_floats(const NlamMlp* m, int64_t n_rows, int B);
-int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* out, int64_t n_rows, int B, cudaStream_t st,
-                   float* ws);
+int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows, int B,
+                   cudaStream_t st, float* ws);
 bool tc_inet_gen_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, int flags, const float* send,
                            int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs);
 size_t tc_inet_gen_workspace_floats(const NlamGraph* g, int B, int H);

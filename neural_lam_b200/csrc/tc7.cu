@@ -446,9 +446,14 @@ int tc_mlp2(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSr
 
 // ---- narrow / concatenated inputs (grid embedder: prev | prev_prev | forcing | static, reference graph/base.py:275-283)
 // at H = 128 / 256: the sources are packed into one zero-padded dense (rows, Kp) block first, then the two Linear launches
+// (a source with a row index gathers: row r of the block is row idx[r] of the source — the [e | x_src | x_dst] rows of an
+// edge MLP whose per-chunk weights rule out the fused edge kernels: SplitMLPs, reference gnn_layers.py:274-324)
+struct PackIdx {
+  const int32_t* i[4];
+};
 __global__ void pack_rows_kernel(const float* s0, const float* s1, const float* s2, const float* s3, int d0, int d1, int d2,
                                  int d3, long long bs0, long long bs1, long long bs2, long long bs3, float* out, int kp,
-                                 long long n_rows, int B) {
+                                 long long n_rows, int B, PackIdx ix) {
   const long long total = (long long)B * n_rows * kp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % kp);
@@ -456,23 +461,21 @@ __global__ void pack_rows_kernel(const float* s0, const float* s1, const float* 
     const int b = (int)(i / ((long long)kp * n_rows));
     float v = 0.f;
     int cc = c;
-    if (cc < d0) v = s0[b * bs0 + r * d0 + cc];
-    else if ((cc -= d0) < d1) v = s1[b * bs1 + r * d1 + cc];
-    else if ((cc -= d1) < d2) v = s2[b * bs2 + r * d2 + cc];
-    else if ((cc -= d2) < d3) v = s3[b * bs3 + r * d3 + cc];
+    if (cc < d0) v = s0[b * bs0 + (ix.i[0] ? (long long)ix.i[0][r] : r) * d0 + cc];
+    else if ((cc -= d0) < d1) v = s1[b * bs1 + (ix.i[1] ? (long long)ix.i[1][r] : r) * d1 + cc];
+    else if ((cc -= d1) < d2) v = s2[b * bs2 + (ix.i[2] ? (long long)ix.i[2][r] : r) * d2 + cc];
+    else if ((cc -= d2) < d3) v = s3[b * bs3 + (ix.i[3] ? (long long)ix.i[3][r] : r) * d3 + cc];
     out[i] = v;
   }
 }
 
 bool tc_mlp2_packed_supported(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, const NlamRowSrc* res2) {
-  if (m->n_linear != 2 || res || res2 || n_src < 1 || n_src > 4) return false;
+  if (m->n_linear != 2 || res2 || n_src < 1 || n_src > 4) return false;
   const int H = m->out_dim[0], no = m->out_dim[1];
-  if (!(H == 128 || H == 256) || no < 1 || no > 256 || (m->ln_gamma && no != npad(no))) return false;
+  if (!(H == 64 || H == 128 || H == 256) || no < 1 || no > 256 || (m->ln_gamma && no != npad(no))) return false;
+  if (res && (res->dim != no || no != npad(no) || res->bstride % 4 != 0 || !aligned16(res->ptr))) return false;
   int k = 0;
-  for (int s = 0; s < n_src; ++s) {
-    if (srcs[s].idx) return false;
-    k += srcs[s].dim;
-  }
+  for (int s = 0; s < n_src; ++s) k += srcs[s].dim;  // sources may gather (row index)
   return k == m->in_dim && k % 4 == 0 && k <= 1024 && aligned16(m->w[0]) && aligned16(m->w[1]);
 }
 
@@ -481,24 +484,26 @@ size_t tc_mlp2_packed_workspace_floats(const NlamMlp* m, int64_t n_rows, int B) 
   return (size_t)n_rows * B * (kp + m->out_dim[0]);
 }
 
-int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* out, int64_t n_rows, int B, cudaStream_t st,
-                   float* ws) {
+int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, float* out, int64_t n_rows, int B,
+                   cudaStream_t st, float* ws) {
   const int kp = (m->in_dim + 31) / 32 * 32, H = m->out_dim[0], no = m->out_dim[1];
   float* packed = ws;
   float* hid = ws + (size_t)n_rows * B * kp;
   const float* sp[4] = {nullptr, nullptr, nullptr, nullptr};
   int d[4] = {0, 0, 0, 0};
   long long bs[4] = {0, 0, 0, 0};
+  PackIdx ix = {{nullptr, nullptr, nullptr, nullptr}};
   for (int s = 0; s < n_src; ++s) {
     sp[s] = srcs[s].ptr;
     d[s] = srcs[s].dim;
     bs[s] = B > 1 ? srcs[s].bstride : 0;
+    ix.i[s] = srcs[s].idx;
   }
   const long long total = (long long)B * n_rows * kp;
   {
     ProfScope ps("pack_rows_kernel", st, 4.0 * total + 4.0 * (double)B * n_rows * m->in_dim);
     pack_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
-        sp[0], sp[1], sp[2], sp[3], d[0], d[1], d[2], d[3], bs[0], bs[1], bs[2], bs[3], packed, kp, n_rows, B);
+        sp[0], sp[1], sp[2], sp[3], d[0], d[1], d[2], d[3], bs[0], bs[1], bs[2], bs[3], packed, kp, n_rows, B, ix);
   }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());
@@ -511,6 +516,14 @@ int tc_mlp2_packed(const NlamMlp* m, const NlamRowSrc* srcs, int n_src, float* o
   memset(&c, 0, sizeof(c));
   c.x0 = hid; c.x0_bs = (int64_t)n_rows * H; c.k0 = H; c.w = m->w[1]; c.ldw = H; c.bias = m->b[1]; c.n_out = no;
   c.gamma = m->ln_gamma; c.beta = m->ln_beta; c.eps = m->ln_eps; c.n_rows = n_rows; c.B = B; c.out = out;
+  if (res && res->idx) {  // gathered residual (PropagationNet: + x_src)
+    c.post = res->ptr;
+    c.post_idx = res->idx;
+    c.post_bs = B > 1 ? res->bstride : 0;
+  } else if (res) {
+    c.res = res->ptr;
+    c.res_bs = B > 1 ? res->bstride : 0;
+  }
   return tc_linear(c, st);
 }
 
@@ -526,7 +539,7 @@ extern "C" int nlam_pack_rows(const float* s0, const float* s1, const float* s2,
   {
     nlam::ProfScope ps("pack_rows_kernel", st, 8.0 * total);
     nlam::pack_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
-        s0, s1, s2, s3, d0, d1, d2, d3, bs0, bs1, bs2, bs3, out, kp, n_rows, B);
+        s0, s1, s2, s3, d0, d1, d2, d3, bs0, bs1, bs2, bs3, out, kp, n_rows, B, nlam::PackIdx{{nullptr, nullptr, nullptr, nullptr}});
   }
   nlam::count_launch();
   NLAM_CUDA_OK(cudaGetLastError());

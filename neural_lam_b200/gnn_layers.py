@@ -218,7 +218,7 @@ class InteractionNet(nn.Module):
     def _kernel_messages(self, send, rec, edge):
         """Messages in ORIGINAL edge order + aggregate, composed from the row-MLP and
         segment-sum kernels (used for SplitMLPs layers and ``propagate``)."""
-        fl = self._math_only_flags() if self._fusable() else _lib.MATH_FP32
+        fl = self._math_only_flags()  # SplitMLPs chunks: gather-pack + the generic tcgen05 Linear kernel (or exact fp32)
         idx = [None, self._src32, self._dst32]
         outs = []
         for m, r0, r1 in _mlp_chunks(self.edge_mlp, self.num_edges):
@@ -231,7 +231,7 @@ class InteractionNet(nn.Module):
         return aggr, msg
 
     def _kernel_node_update(self, rec, aggr):
-        fl = self._math_only_flags() if self._fusable() else _lib.MATH_FP32
+        fl = self._math_only_flags()
         base = aggr if self.propagation else rec
         outs = []
         for m, r0, r1 in _mlp_chunks(self.aggr_mlp, self.num_rec):

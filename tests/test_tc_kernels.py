@@ -565,3 +565,27 @@ def test_chained_node_update_output_map_step_epilogue(with_boundary, B, G):
         m = mask.double().cpu()
         new = m * bnd.double().cpu() + (1 - m) * new
     assert (got.double().cpu() - new).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("cls_name,H", [("InteractionNet", 64), ("PropagationNet", 64), ("InteractionNet", 128)])
+def test_split_mlps_layer_on_tensor_cores(cls_name, H):
+    """SplitMLPs layers (reference gnn_layers.py:274-324; HiLAMParallel's per-level MLPs): every chunk's edge MLP runs as
+    gather-pack + two launches of the generic tcgen05 Linear kernel, the node MLPs on the row-MLP kernels — no SIMT math."""
+    cls = getattr(nlb, cls_name)
+    ns, nr, ne, B = 70, 50, 600, 2
+    ei = _graph(ns, nr, ne, 4, False)  # chunks are defined on the layer's own (unsorted) edge order
+    torch.manual_seed(5)
+    ech, ach = [250, 350], [20, 30]
+    net = cls(ei, H, edge_chunk_sizes=ech, aggr_chunk_sizes=ach, math="tf32")
+    send, rec, edge = torch.randn(B, ns, H), torch.randn(B, nr, H), torch.randn(B, ne, H)
+    prop = cls_name == "PropagationNet"
+    want = rp.interaction_net({k: v.double() for k, v in net.state_dict().items()}, ei, send.double(), rec.double(),
+                              edge.double(), propagation=prop, aggr="mean" if prop else "sum",
+                              edge_chunk_sizes=ech, aggr_chunk_sizes=ach)
+    net = net.to(DEV)
+    with torch.no_grad(), ops.profile_launches() as prof:
+        got = net(send.to(DEV), rec.to(DEV), edge.to(DEV))
+    assert not any("simt" in n for n in prof.names()), prof.names()
+    assert any(n.startswith("tc_linear") for n in prof.names()), prof.names()
+    err = max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want))
+    assert err <= 2e-2, err
