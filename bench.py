@@ -646,8 +646,16 @@ def run_ours(args):
         kernels = kernel_table(fc, bufs, peak)
         train = None
         if not args.no_train:
-            with torch.enable_grad():
-                train = measure_train_step(model, device)
+            # reference default batch 4 (train_model.py:261-263); the 1024^2 H=256 workload trains one sample per GPU
+            tb = 1 if args.config == 4 else 4
+            try:
+                with torch.enable_grad():
+                    train = measure_train_step(model, device, B=tb)
+            except torch.OutOfMemoryError as e:  # recompute-in-backward workspaces of the largest layer
+                train = {"batch": tb, "unavailable": "out of device memory: " + str(e).split(".")[0]}
+                for p_ in model.parameters():
+                    p_.grad = None
+                torch.cuda.empty_cache()
         parity = None if args.no_parity else parity_check(model, fc, device)
         ref_cuda = None
         if not args.no_ref_cuda:
