@@ -147,6 +147,18 @@ int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* ag
                   float* aggr_out, int B, int flags, void* workspace, size_t ws_bytes,
                   void* stream);
 
+/* Stack of InteractionNet layers over ONE node set (send == rec: the mesh processor, reference graph_lam.py:117-126).  With
+ * next_edge_mlp + proj_out the node update of this call also computes the node projections of the NEXT layer's edge MLP,
+ * P_s = W1s'·x', P_r = W1r'·x' + b1' (proj_out: (2, B, n_rec, 64)), in the same kernel (csrc/tc10.cu); with proj_in the edge stage
+ * of this call takes its projections from the previous call instead of launching its own projection pass.  Both NULL: exactly
+ * nlam_inet_fwd.  nlam_inet_chain_supported says whether a call shape can be a consumer (next_edge_mlp NULL) and a producer. */
+int nlam_inet_chain_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const NlamMlp* next_edge_mlp,
+                              const float* send, int64_t send_bstride, const float* rec, int64_t rec_bstride, int B, int flags);
+int nlam_inet_fwd_chain(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const NlamMlp* next_edge_mlp,
+                        const float* send, int64_t send_bstride, const float* rec, int64_t rec_bstride, const float* edge,
+                        int64_t edge_bstride, float* rec_out, float* edge_out, float* aggr_out, const float* proj_in,
+                        float* proj_out, int B, int flags, void* workspace, size_t ws_bytes, void* stream);
+
 /* 1 if nlam_inet_fwd with these arguments may be called with edge_out == edge (tensor-core path with node projections on a
  * general CSR edge set, dense batches: the update is a TMA reduce-add of the message tiles, csrc/tc8.cu), else 0. */
 int nlam_inet_inplace_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bstride,

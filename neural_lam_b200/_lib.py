@@ -91,6 +91,14 @@ SYMBOLS = {
     "nlam_graph_sptr": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nlam_graph_sperm": (ctypes.c_void_p, [ctypes.c_void_p]),
     "nlam_inet_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "nlam_inet_chain_supported": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamMlp), ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                                 ctypes.c_int]),
+    "nlam_inet_fwd_chain": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.POINTER(NlamMlp), ctypes.POINTER(NlamMlp), ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "nlam_inet_inplace_supported": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(NlamMlp), ctypes.c_void_p, ctypes.c_int64,
                                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                                    ctypes.c_int, ctypes.c_int]),

@@ -108,11 +108,54 @@ extern "C" int nlam_inet_inplace_supported(const NlamGraph* g, const NlamMlp* ed
   return inplace_path(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, B, flags) ? 1 : 0;
 }
 
+// chain of layers over ONE node set (the mesh processor): can this call consume node projections computed by the previous
+// layer's node kernel and, with next_mlp, produce those of the next layer (tc10.cu)?
+static bool chain_path(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const NlamMlp* next_mlp,
+                       const float* send, int64_t send_bs, const float* rec, int64_t rec_bs, int B, int flags) {
+  if (!(want_tf32(flags) && tc_edge_supported(g, edge_mlp, flags)) || (flags & (NLAM_PROPAGATION | NLAM_EDGE_ONLY))) return false;
+  if (send != rec || send_bs != rec_bs || g->n_send != g->n_rec || (B > 1 && rec_bs != g->n_rec * 64)) return false;
+  if (tc_ell_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, true)) return false;
+  if (!tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, g->n_send)) return false;
+  if (next_mlp && !tc_node_proj_supported(aggr_mlp, next_mlp, rec, rec_bs, rec, g->n_rec, rec, rec)) return false;
+  return true;
+}
+
+extern "C" int nlam_inet_chain_supported(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
+                                         const NlamMlp* next_edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                                         int64_t rec_bs, int B, int flags) {
+  if (!g || !edge_mlp || !aggr_mlp || !send || !rec || B < 1 || edge_mlp->n_linear < 1) return 0;
+  return chain_path(g, edge_mlp, aggr_mlp, next_edge_mlp, send, send_bs, rec, rec_bs, B, flags) ? 1 : 0;
+}
+
+static int inet_fwd_impl(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const NlamMlp* next_mlp,
+                         const float* send, int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs,
+                         float* rec_out, float* edge_out, float* aggr_out, const float* proj_in, float* proj_out, int B, int flags,
+                         void* workspace, size_t ws_bytes, void* stream);
+
 extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
                              const float* send, int64_t send_bs, const float* rec, int64_t rec_bs,
                              const float* edge, int64_t edge_bs, float* rec_out, float* edge_out,
                              float* aggr_out, int B, int flags, void* workspace, size_t ws_bytes,
                              void* stream) {
+  return inet_fwd_impl(g, edge_mlp, aggr_mlp, nullptr, send, send_bs, rec, rec_bs, edge, edge_bs, rec_out, edge_out, aggr_out,
+                       nullptr, nullptr, B, flags, workspace, ws_bytes, stream);
+}
+
+extern "C" int nlam_inet_fwd_chain(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp,
+                                   const NlamMlp* next_edge_mlp, const float* send, int64_t send_bs, const float* rec,
+                                   int64_t rec_bs, const float* edge, int64_t edge_bs, float* rec_out, float* edge_out,
+                                   float* aggr_out, const float* proj_in, float* proj_out, int B, int flags, void* workspace,
+                                   size_t ws_bytes, void* stream) {
+  NLAM_REQUIRE((next_edge_mlp != nullptr) == (proj_out != nullptr), NLAM_E_INVALID,
+               "nlam_inet_fwd_chain: next_edge_mlp and proj_out go together");
+  return inet_fwd_impl(g, edge_mlp, aggr_mlp, next_edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, rec_out, edge_out, aggr_out,
+                       proj_in, proj_out, B, flags, workspace, ws_bytes, stream);
+}
+
+static int inet_fwd_impl(const NlamGraph* g, const NlamMlp* edge_mlp, const NlamMlp* aggr_mlp, const NlamMlp* next_mlp,
+                         const float* send, int64_t send_bs, const float* rec, int64_t rec_bs, const float* edge, int64_t edge_bs,
+                         float* rec_out, float* edge_out, float* aggr_out, const float* proj_in, float* proj_out, int B, int flags,
+                         void* workspace, size_t ws_bytes, void* stream) {
   const bool edge_only = flags & NLAM_EDGE_ONLY;
   NLAM_REQUIRE(g && edge_mlp && aggr_mlp && send && rec && edge && (rec_out || edge_only), NLAM_E_INVALID,
                "nlam_inet_fwd: null argument");
@@ -122,6 +165,11 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   NLAM_REQUIRE(edge_mlp->in_dim == 3 * H && aggr_mlp->in_dim == 2 * H &&
                    aggr_mlp->out_dim[aggr_mlp->n_linear - 1] == H,
                NLAM_E_INVALID, "nlam_inet_fwd: MLP widths inconsistent with H=%d", H);
+  const bool chained = proj_in || next_mlp;
+  NLAM_REQUIRE(!chained || chain_path(g, edge_mlp, aggr_mlp, next_mlp, send, send_bs, rec, rec_bs, B, flags), NLAM_E_UNSUPPORTED,
+               "nlam_inet_fwd_chain: call shape without a chained path (see nlam_inet_chain_supported)");
+  NLAM_REQUIRE(!next_mlp || ((((uintptr_t)rec_out | (uintptr_t)proj_out) & 15) == 0), NLAM_E_INVALID,
+               "nlam_inet_fwd_chain: unaligned outputs");
   NLAM_REQUIRE(edge_out != edge || inplace_path(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, B, flags),
                NLAM_E_INVALID, "nlam_inet_fwd: edge_out aliases edge for a call shape without in-place support "
                "(see nlam_inet_inplace_supported)");
@@ -158,10 +206,12 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
     } else if (tc_edge2_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, B, send_rows)) {
       // split first Linear: node projections + K=64 edge kernel with sender windows (tc5.cu)
       // (tc8.cu when the edge tensor is updated in place or not written at all)
+      // (projections computed by the previous layer's node kernel: proj_in holds [P_s | P_r] in the scratch layout)
+      float* pws = proj_in ? const_cast<float*>(proj_in) : scratch;
       if (tc_edge_rmw_supported(g, edge, edge_bs, edge_out, B))
-        rc = tc_edge_rmw(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
+        rc = tc_edge_rmw(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, pws, proj_in != nullptr);
       else
-        rc = tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, scratch);
+        rc = tc_edge3(g, edge_mlp, send, send_bs, rec, rec_bs, edge, edge_bs, edge_out, aggr, B, flags, st, pws, proj_in != nullptr);
     } else if (tc_edge_bcast_supported(g, edge_mlp, flags, send, send_bs, rec, rec_bs, edge, edge_bs, B, edge_out != nullptr)) {
       // batch-broadcast edge features and receivers, large sender set, no edge update (grid -> mesh): tile-major
       // kernel with the edge term resident in TMEM and raw sender rows gathered (tc6.cu)
@@ -185,6 +235,8 @@ extern "C" int nlam_inet_fwd(const NlamGraph* g, const NlamMlp* edge_mlp, const 
   // node update: rec' = base + aggr_mlp(cat(rec, aggr)); base = rec (InteractionNet) or aggr (PropagationNet)
   NlamRowSrc nsrcs[2] = {{rec, nullptr, rec_bs, H, 0}, {aggr, nullptr, aggr_bs, H, 0}};
   NlamRowSrc nres = prop ? nsrcs[1] : nsrcs[0];
+  if (next_mlp)  // node update + the next layer's node projections (tc10.cu)
+    return tc_node_proj(aggr_mlp, next_mlp, rec, rec_bs, aggr, g->n_rec, B, rec_out, proj_out, st);
   if (use_tc && tc_rowmlp_supported(aggr_mlp, nsrcs, 2, &nres, nullptr, g->n_rec))
     return tc_rowmlp(aggr_mlp, nsrcs, 2, &nres, rec_out, g->n_rec, B, st);
   return rowmlp_simt(aggr_mlp, nsrcs, 2, &nres, nullptr, rec_out, nullptr, g->n_rec, B, st);

@@ -127,17 +127,22 @@ int tc_edge_bcast(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send
 // tc5.cu
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-             cudaStream_t stream, float* ws);
+             cudaStream_t stream, float* ws, bool have_proj = false);
 // tc8.cu: same math, edge tensor updated in place (TMA reduce-add) or not written at all
 bool tc_edge_rmw_supported(const NlamGraph* g, const float* edge, int64_t edge_bs, const float* edge_out, int B);
 int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
                 int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-                cudaStream_t stream, float* ws);
+                cudaStream_t stream, float* ws, bool have_proj = false);
 // tc9.cu: node update of the mesh->grid layer + output_map + step epilogue in one kernel
 bool tc_node_out_supported(const NlamMlp* node_mlp, const NlamMlp* out_mlp, const float* rec, int64_t rec_bs, const float* aggr,
                            int64_t n_rows, int B, const float* out, const StepEpilogue* ep);
 int tc_node_out(const NlamMlp* node_mlp, const NlamMlp* out_mlp, const float* rec, int64_t rec_bs, const float* aggr,
                 int64_t n_rows, int B, float* out, const StepEpilogue* ep, cudaStream_t st);
+// tc10.cu: node update + the next layer's node projections in one kernel (stacks of layers over one node set)
+bool tc_node_proj_supported(const NlamMlp* node_mlp, const NlamMlp* next_edge_mlp, const float* rec, int64_t rec_bs,
+                            const float* aggr, int64_t n_rows, const float* out, const float* proj_out);
+int tc_node_proj(const NlamMlp* node_mlp, const NlamMlp* next_edge_mlp, const float* rec, int64_t rec_bs, const float* aggr,
+                 int64_t n_rows, int B, float* out, float* proj_out, cudaStream_t st);
 // tc4.cu
 bool tc_rowmlp64_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const NlamRowSrc* res, int64_t n_rows);
 bool tc_rowmlp_narrow_out_supported(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, int64_t n_rows, const float* out,

@@ -512,7 +512,7 @@ int edge_projections(const float* send, int64_t send_bs, int64_t ns, int Bs, con
 
 int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
              int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-             cudaStream_t st, float* ws) {
+             cudaStream_t st, float* ws, bool have_proj) {
   NLAM_REQUIRE(aligned16(edge) && aligned16(aggr_out) && (!edge_out || aligned16(edge_out)) && edge_bs % 4 == 0 &&
                    aligned16(ws),
                NLAM_E_INVALID, "tc_edge3: pointers / strides must be 16-byte aligned");
@@ -522,7 +522,8 @@ int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
   float* Ps = ws;
   float* Pr = ws + (size_t)Bs * ns * 64;
   const float* w1 = edge_mlp->w[0];  // (64, 192): columns [e | sender | receiver]
-  int rc = edge_projections(send, send_bs, ns, Bs, rec, rec_bs, nr, Br, w1, edge_mlp->b[0], Ps, Pr, st);
+  // have_proj: ws already holds [P_s | P_r] of this edge MLP (written by the previous layer's node kernel, tc10.cu)
+  int rc = have_proj ? NLAM_OK : edge_projections(send, send_bs, ns, Bs, rec, rec_bs, nr, Br, w1, edge_mlp->b[0], Ps, Pr, st);
   if (rc) return rc;
 
   CUtensorMap me, mw1, mw2, mo, mps;

@@ -540,7 +540,7 @@ bool tc_edge_rmw_supported(const NlamGraph* g, const float* edge, int64_t edge_b
 
 int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int64_t send_bs, const float* rec,
                 int64_t rec_bs, const float* edge, int64_t edge_bs, float* edge_out, float* aggr_out, int B, int flags,
-                cudaStream_t st, float* ws) {
+                cudaStream_t st, float* ws, bool have_proj) {
   NLAM_REQUIRE(aligned16(edge) && aligned16(aggr_out) && edge_bs % 4 == 0 && aligned16(ws), NLAM_E_INVALID,
                "tc_edge_rmw: pointers / strides must be 16-byte aligned");
   NLAM_REQUIRE(!edge_out || edge_out == edge, NLAM_E_INVALID, "tc_edge_rmw: the edge output must alias the edge input");
@@ -550,7 +550,8 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   float* Ps = ws;
   float* Pr = ws + (size_t)Bs * ns * 64;
   const float* w1 = edge_mlp->w[0];  // (64, 192): columns [e | sender | receiver]
-  int rc = edge_projections(send, send_bs, ns, Bs, rec, rec_bs, nr, Br, w1, edge_mlp->b[0], Ps, Pr, st);
+  // have_proj: ws already holds [P_s | P_r] of this edge MLP (written by the previous layer's node kernel, tc10.cu)
+  int rc = have_proj ? NLAM_OK : edge_projections(send, send_bs, ns, Bs, rec, rec_bs, nr, Br, w1, edge_mlp->b[0], Ps, Pr, st);
   if (rc) return rc;
 
   CUtensorMap me, mw1, mw2, mps;

@@ -19,6 +19,8 @@ _DEFAULT_MATH = "auto"
 # in-place edge update of the middle layers of a no-grad stack (csrc/tc8.cu: TMA reduce-add of the message tiles); the
 # library decides per call shape (nlam_inet_inplace_supported), other shapes stay out of place
 _INPLACE_EDGE_UPDATE = True
+# the node kernel of a stacked layer also computes the next layer's node projections (csrc/tc10.cu)
+_CHAIN_PROJECTIONS = True
 _MATH_FLAGS = {"auto": 0, "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}
 
 
@@ -333,22 +335,40 @@ class InteractionNet(nn.Module):
             return outs[0], outs[1]
         return outs[0]
 
+    def _stackable(self):
+        return self._halo is None and self.update_edges and self._fusable() and self._is_sorted and not self.propagation
+
     @torch.no_grad()
-    def forward_stacked(self, node_rep, edge_rep, first, last):
+    def forward_stacked(self, node_rep, edge_rep, first, last, proj_in=None, next_layer=None):
         """Inference-only entry for a layer inside a stack over ONE node set whose intermediate edge tensors are
         private to the stack (``GNNSequential`` with ``keep_edge_rep=False``): the last layer does not write its
         edge output (nobody reads it), a middle layer may update ``edge_rep`` in place (``first``: the incoming
         tensor belongs to the caller — e.g. the cached static embedding — and is never written).  Same values as
-        ``forward``.  Returns ``(node_rep', edge_rep' | None)``."""
+        ``forward``.  ``proj_in``: this layer's node projections, computed by the previous layer's node kernel;
+        ``next_layer``: the following layer of the stack — when the library supports it for both, this call's node kernel
+        also computes that layer's projections (csrc/tc10.cu).  Returns ``(node_rep', edge_rep' | None, proj_next | None)``."""
         if self._halo is not None or not (self.update_edges and self._fusable() and self._is_sorted):
-            return self.forward(node_rep, node_rep, edge_rep)
+            assert proj_in is None
+            return (*self.forward(node_rep, node_rep, edge_rep), None)
         self._check_inputs(node_rep, node_rep, edge_rep)
         _, (s3, r3, e3) = self._batchify(node_rep, node_rep, edge_rep)
         g = self._graph(r3.device)
         inplace = _INPLACE_EDGE_UPDATE and (not first) and (not last) and e3.is_contiguous()
-        rec_out, edge_out, _ = ops.inet_fwd(g, self.edge_mlp, self.aggr_mlp, s3, r3, e3, not last, self._flags(),
-                                            edge_inplace=inplace)
-        return rec_out, edge_out
+        nxt = None
+        if (_CHAIN_PROJECTIONS and next_layer is not None and isinstance(next_layer, InteractionNet) and next_layer._stackable()
+                and self._stackable() and next_layer.num_rec == self.num_rec and r3.shape[0] > 0):
+            fl = self._flags()
+            if (ops.inet_chain_supported(g, self.edge_mlp, self.aggr_mlp, next_layer.edge_mlp, r3, fl)
+                    and ops.inet_chain_supported(next_layer._graph(r3.device), next_layer.edge_mlp, next_layer.aggr_mlp, None, r3,
+                                                 next_layer._flags())):
+                nxt = next_layer.edge_mlp
+        if proj_in is None and nxt is None:
+            rec_out, edge_out, _ = ops.inet_fwd(g, self.edge_mlp, self.aggr_mlp, s3, r3, e3, not last, self._flags(),
+                                                edge_inplace=inplace)
+            return rec_out, edge_out, None
+        rec_out, edge_out, _, proj_out = ops.inet_fwd(g, self.edge_mlp, self.aggr_mlp, s3, r3, e3, not last, self._flags(),
+                                                      edge_inplace=inplace, proj_in=proj_in, next_edge_seq=nxt)
+        return rec_out, edge_out, proj_out
 
     @torch.no_grad()
     def aggregate_only(self, send_rep, rec_rep, edge_rep):

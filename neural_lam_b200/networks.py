@@ -119,11 +119,15 @@ class GNNSequential(nn.Module):
         reference graph_lam.py:185 ``mesh_rep, _ = self.processor(...)``): in no-grad mode the last layer then
         skips writing it, and the layers in between update their (private) edge tensor IN PLACE."""
         fast = (not keep_edge_rep) and not torch.is_grad_enabled()
+        proj = None  # node projections of the next layer's edge MLP, computed by the previous layer's node kernel
         for i in range(self._n):
             mod = getattr(self, f"module_{i}")
             if fast and hasattr(mod, "forward_stacked"):
-                mesh_rep, edge_rep = mod.forward_stacked(mesh_rep, edge_rep, first=(i == 0), last=(i == self._n - 1))
+                nxt = getattr(self, f"module_{i + 1}") if i + 1 < self._n else None
+                mesh_rep, edge_rep, proj = mod.forward_stacked(mesh_rep, edge_rep, first=(i == 0), last=(i == self._n - 1),
+                                                               proj_in=proj, next_layer=nxt)
             else:
+                assert proj is None
                 mesh_rep, edge_rep = mod(mesh_rep, mesh_rep, edge_rep)
         return mesh_rep, edge_rep
 

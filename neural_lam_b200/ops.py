@@ -292,11 +292,14 @@ class SegmentSumFn(torch.autograd.Function):
 
 
 def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags, want_aggr=False, edge_inplace=False,
-             edge_only=False):
+             edge_only=False, proj_in=None, next_edge_seq=None):
     """One fused InteractionNet/PropagationNet forward through ``nlam_inet_fwd``.
     ``edge_csr`` must be in CSR edge order.  ``edge_inplace``: write e' = e + m over ``edge_csr`` itself (a dense
     batched tensor the caller owns).  ``edge_only``: stop after the aggregation (``NLAM_EDGE_ONLY``; the node update runs in a
-    later call, see ``node_update_step``); rec_out is None then.  Returns (rec_out, edge_out|None, aggr|None), 3-D."""
+    later call, see ``node_update_step``); rec_out is None then.  ``proj_in`` / ``next_edge_seq``: chained stack over one node
+    set (``nlam_inet_fwd_chain``; check ``inet_chain_supported`` first): take this layer's node projections from the previous
+    call, and let the node kernel compute those of the next layer's edge MLP — a 4th return value ``proj_out`` then.
+    Returns (rec_out, edge_out|None, aggr|None), 3-D."""
     L = _lib.lib()
     s, Bs, sbs = as_rows(send)
     r, Br, rbs = as_rows(rec)
@@ -330,6 +333,17 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
     hint = _lib.HINT_ONE_HIDDEN if (em.n_linear == 2 and am.n_linear == 2 and em.ln_gamma and am.ln_gamma) else 0
     ws_bytes = L.nlam_inet_workspace_bytes(graph.handle, B, H, flags | hint)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    if proj_in is not None or next_edge_seq is not None:
+        nm = mlp_struct(next_edge_seq) if next_edge_seq is not None else None
+        proj_out = torch.empty((2, B, graph.n_rec, H), device=dev, dtype=torch.float32) if nm is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(L.nlam_inet_fwd_chain(
+                graph.handle, ctypes.byref(em), ctypes.byref(am), ctypes.byref(nm) if nm is not None else None,
+                s.data_ptr(), sbs, r.data_ptr(), rbs, e.data_ptr(), ebs,
+                rec_out.data_ptr(), edge_out.data_ptr() if update_edges else None,
+                aggr.data_ptr() if want_aggr else None, proj_in.data_ptr() if proj_in is not None else None,
+                proj_out.data_ptr() if proj_out is not None else None, B, flags, ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
+        return rec_out, edge_out, aggr, proj_out
     with torch.cuda.device(dev):
         _lib.check(L.nlam_inet_fwd(
             graph.handle, ctypes.byref(em), ctypes.byref(am),
@@ -338,6 +352,20 @@ def inet_fwd(graph, edge_seq, aggr_seq, send, rec, edge_csr, update_edges, flags
             aggr.data_ptr() if want_aggr else None, B, flags | (_lib.EDGE_ONLY if edge_only else 0),
             ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
     return rec_out, edge_out, aggr
+
+
+def inet_chain_supported(graph, edge_seq, aggr_seq, next_edge_seq, node_rep, flags):
+    """Can ``inet_fwd`` on this layer of a stack over one node set consume projections of the previous call and (with
+    ``next_edge_seq``) produce the next layer's (``nlam_inet_chain_supported``)?"""
+    L = _lib.lib()
+    x, B, bs = as_rows(node_rep)
+    if not x.is_cuda:
+        return False
+    em, am = mlp_struct(edge_seq), mlp_struct(aggr_seq)
+    nm = mlp_struct(next_edge_seq) if next_edge_seq is not None else None
+    return bool(L.nlam_inet_chain_supported(graph.handle, ctypes.byref(em), ctypes.byref(am),
+                                            ctypes.byref(nm) if nm is not None else None, x.data_ptr(), bs, x.data_ptr(), bs, B,
+                                            flags))
 
 
 def step_epilogue(net_out, prev, boundary, bmask, diff_std, diff_mean, out=None, clamp=None):

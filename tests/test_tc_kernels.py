@@ -519,6 +519,10 @@ def test_stack_updates_private_edge_tensor_in_place():
             got, e_none = seq(x, e_in, keep_edge_rep=False)
     assert e_none is None
     assert prof.names().count("tc_edge_rmw_kernel") == 3 and prof.names().count("tc_edge3_kernel") == 1, prof.names()
+    # the node kernel of layers 1-3 also computes the next layer's node projections (tc10.cu): one projection launch (layer 1)
+    # and one plain node update (layer 4) remain
+    assert prof.names().count("tc_node_proj_kernel") == 3 and prof.names().count("tc_rowlinear_kernel") == 1, prof.names()
+    assert len(prof.names()) == 9, prof.names()
     assert torch.equal(e_static, keep)
     assert (got - want).abs().max().item() <= 5e-3
 
@@ -589,3 +593,37 @@ def test_split_mlps_layer_on_tensor_cores(cls_name, H):
     assert any(n.startswith("tc_linear") for n in prof.names()), prof.names()
     err = max((g.double().cpu() - w).abs().max().item() for g, w in zip(got, want))
     assert err <= 2e-2, err
+
+
+@pytest.mark.parametrize("B,N", [(1, 100), (3, 500), (2, 128 * 3 + 5)])
+def test_node_kernel_with_next_layer_projections(B, N):
+    """tc10.cu through nlam_inet_fwd_chain: layer 1 produces the node projections of layer 2's edge MLP in its node kernel, layer
+    2 consumes them — against the unchained calls on the same inputs (same TF32 products: results agree to fp32 rounding)."""
+    ei = _graph(N, N, 9 * N, 7, True)
+    torch.manual_seed(4)
+    l1 = nlb.InteractionNet(ei, 64, math="tf32").to(DEV)
+    l2 = nlb.InteractionNet(ei, 64, math="tf32").to(DEV)
+    with torch.no_grad():
+        for p in list(l1.parameters()) + list(l2.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, N, 64, device=DEV)
+    e = torch.randn(B, 9 * N, 64, device=DEV)
+    with torch.no_grad():
+        x1, e1 = l1(x, x, e)
+        x2, e2 = l2(x1, x1, e1)
+        with ops.profile_launches() as prof:
+            y1, f1, proj = l1.forward_stacked(x, e.clone(), first=True, last=False, next_layer=l2)
+            assert proj is not None and proj.shape == (2, B, N, 64)
+            y2, f2, none = l2.forward_stacked(y1, f1, first=False, last=True, proj_in=proj)
+        assert none is None and f2 is None
+    assert prof.names().count("tc_node_proj_kernel") == 1 and prof.names().count("tc_rowlinear_kernel") == 1, prof.names()
+    assert (y1 - x1).abs().max().item() <= 1e-5 and (f1 - e1).abs().max().item() <= 1e-5
+    assert (y2 - x2).abs().max().item() <= 2e-3
+    # the projections themselves against fp64
+    w = l2.edge_mlp[0].weight.double().cpu()
+    b = l2.edge_mlp[0].bias.double().cpu()
+    ps = y1.double().cpu() @ w[:, 64:128].T
+    pr = y1.double().cpu() @ w[:, 128:192].T + b
+    assert (proj[0].double().cpu() - ps).abs().max().item() <= 1e-2
+    assert (proj[1].double().cpu() - pr).abs().max().item() <= 1e-2
