@@ -116,6 +116,8 @@ tc_node_proj_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPr) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     s_gamma[tid] = p.gamma[tid];
     s_beta[tid] = p.beta[tid];
@@ -495,7 +497,7 @@ int tc_node_proj(const NlamMlp* node_mlp, const NlamMlp* next_edge_mlp, const fl
     const long long rows = (long long)B * n_rows;
     const long long nb = 4LL * 64 * ((batched ? rows : n_rows) + rows) + 4LL * 64 * 3 * rows + 4LL * (64 * 128 + 64 * 64 + 128 * 64 + 64 * 5);
     ProfScope ps("tc_node_proj_kernel", st, nb);
-    tc_node_proj_kernel<<<grid, r10::THREADS, r10::SMEM, st>>>(mr, mg, w1, w2, wp, mo, mps, mpr, p);
+    NLAM_CUDA_OK(launch_pdl(tc_node_proj_kernel, grid, r10::THREADS, r10::SMEM, st, mr, mg, w1, w2, wp, mo, mps, mpr, p));
   }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());

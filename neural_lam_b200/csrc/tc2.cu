@@ -69,6 +69,8 @@ tc_rowlinear_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -212,7 +214,7 @@ int rowlinear_multi(const RowLinProblem* pr, int n_prob, cudaStream_t st) {
     double bytes = 0;
     for (int i = 0; i < n_prob; ++i) bytes += 2.0 * 256.0 * (double)pr[i].n_rows * pr[i].B_eff + 4.0 * (64 * 64 + 64);
     ProfScope ps("tc_rowlinear_kernel", st, bytes);
-    tc_rowlinear_kernel<<<grid, rl::THREADS, rl::SMEM, st>>>(mx[0], mw[0], mo[0], mx[1], mw[1], mo[1], p);
+    NLAM_CUDA_OK(launch_pdl(tc_rowlinear_kernel, grid, rl::THREADS, rl::SMEM, st, mx[0], mw[0], mo[0], mx[1], mw[1], mo[1], p));
   }
   count_launch();
   NLAM_CUDA_OK(cudaGetLastError());

@@ -175,6 +175,8 @@ tc_ell_window_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     sprm[tid] = p.b1[tid];
     sprm[64 + tid] = p.b2[tid];
@@ -701,7 +703,7 @@ int tc_ell_edge(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     if (pf < 0) pf = getenv("NLAM_ELL_NO_PREFETCH") ? 0 : 1;
     q.prefetch = pf;
     ProfScope ps("tc_ell_window_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, false, 64));
-    tc_ell_window_kernel<<<grid, e4::THREADS, e4::SMEM, st>>>(me, mrec, mw1, mw2, mps, mo, q);
+    NLAM_CUDA_OK(launch_pdl(tc_ell_window_kernel, grid, e4::THREADS, e4::SMEM, st, me, mrec, mw1, mw2, mps, mo, q));
   }
   count_launch();
   if (dbg_on) {

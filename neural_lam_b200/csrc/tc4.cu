@@ -146,6 +146,8 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64 && p.in_narrow) {
     int base = 0, col = 0, found = 0;
     int2 e = make_int2(-1, 0);
@@ -702,7 +704,7 @@ int tc_rowmlp64(const NlamMlp* mlp, const NlamRowSrc* srcs, int n_src, const Nla
   {
     ProfScope ps(ep ? "tc_rowmlp64_kernel(step)" : (kind == 2 ? "tc_rowmlp64_kernel(narrow-in)" : "tc_rowmlp64_kernel"), st,
                  rowmlp_algorithmic_bytes(mlp, srcs, n_src, res, nullptr, n_rows, B, false, ep));
-    tc_rowmlp64_kernel<<<grid, r4::THREADS, r4::SMEM, st>>>(a[0], a[1], w1, w2, om, p);
+    NLAM_CUDA_OK(launch_pdl(tc_rowmlp64_kernel, grid, r4::THREADS, r4::SMEM, st, a[0], a[1], w1, w2, om, p));
   }
   count_launch();
   if (dbg_on) {

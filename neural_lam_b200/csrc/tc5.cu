@@ -119,6 +119,8 @@ tc_edge3_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
     if (p.has_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     sprm[tid] = p.b2[tid];
     sprm[64 + tid] = p.gamma[tid];
@@ -588,7 +590,7 @@ int tc_edge3(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, int
   {
     // the node-side terms arrive as projections (same row counts as the raw node rows)
     ProfScope ps("tc_edge3_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
-    tc_edge3_kernel<<<grid, e5::THREADS, e5::SMEM, st>>>(me, mw1, mw2, mo, mps, p);
+    NLAM_CUDA_OK(launch_pdl(tc_edge3_kernel, grid, e5::THREADS, e5::SMEM, st, me, mw1, mw2, mo, mps, p));
   }
   count_launch();
   if (dbg_on) {

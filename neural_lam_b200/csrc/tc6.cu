@@ -142,6 +142,8 @@ tc_edge_bcast_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmXs) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     sprm[tid] = p.b2[tid];
     sprm[64 + tid] = p.gamma[tid];
@@ -642,7 +644,7 @@ int tc_edge_bcast(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send
   }
   {
     ProfScope ps("tc_edge_bcast_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, 0, false, 64));
-    tc_edge_bcast_kernel<<<grid, e6::THREADS, e6::SMEM, st>>>(me, mw1, mw2, mxs, p);
+    NLAM_CUDA_OK(launch_pdl(tc_edge_bcast_kernel, grid, e6::THREADS, e6::SMEM, st, me, mw1, mw2, mxs, p));
   }
   count_launch();
   if (dbg_on) {

@@ -138,6 +138,8 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
     if (p.has_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     sprm[tid] = p.b2[tid];
     sprm[64 + tid] = p.gamma[tid];
@@ -625,9 +627,9 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     ProfScope ps("tc_edge_rmw_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
     // RNOW: segmented sum of an item right after its epilogue 2 (else after epilogue 1 of the group's next item)
     if (rnow)
-      tc_edge_rmw_kernel<true><<<grid, e8::THREADS, e8::SMEM, st>>>(me, mw1, mw2, me, mps, p);
+      NLAM_CUDA_OK(launch_pdl(tc_edge_rmw_kernel<true>, grid, e8::THREADS, e8::SMEM, st, me, mw1, mw2, me, mps, p));
     else
-      tc_edge_rmw_kernel<false><<<grid, e8::THREADS, e8::SMEM, st>>>(me, mw1, mw2, me, mps, p);
+      NLAM_CUDA_OK(launch_pdl(tc_edge_rmw_kernel<false>, grid, e8::THREADS, e8::SMEM, st, me, mw1, mw2, me, mps, p));
   }
   count_launch();
   if (dbg_on) {

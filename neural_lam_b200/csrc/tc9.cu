@@ -139,6 +139,8 @@ tc_node_out_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW4) : "memory");
   }
+  pdl_launch_dependents();
+  pdl_wait();  // everything below may read what the previous kernel in the stream wrote
   if (tid < 64) {
     s_gamma[tid] = p.gamma[tid];
     s_beta[tid] = p.beta[tid];
@@ -639,7 +641,7 @@ int tc_node_out(const NlamMlp* node_mlp, const NlamMlp* out_mlp, const float* re
     if (ep) nb += 4LL * nout * rows * (ep->boundary ? 2 : 1) + (ep->boundary ? 4LL * n_rows : 0);
     nb += 4LL * (64 * 128 + 64 * 64 + 64 * 64 + nout * 64 + 64 * 5 + nout);
     ProfScope ps("tc_node_out_kernel", st, nb);
-    tc_node_out_kernel<<<grid, r9::THREADS, r9::SMEM, st>>>(mr, mg, w1, w2, w3, w4, p);
+    NLAM_CUDA_OK(launch_pdl(tc_node_out_kernel, grid, r9::THREADS, r9::SMEM, st, mr, mg, w1, w2, w3, w4, p));
   }
   count_launch();
   if (dbg_on) {

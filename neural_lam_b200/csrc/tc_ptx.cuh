@@ -64,6 +64,12 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ bool mbar_test_u(uint32_t bar, uint32_t parity) {
   return __shfl_sync(0xffffffffu, (int)mbar_test(bar, parity), 0) != 0;
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute (launch_pdl below)
+// may start while the previous kernel in the stream is still draining; it must not touch anything that kernel writes before
+// pdl_wait() (= the previous grid has completed and its writes are visible).  pdl_launch_dependents() lets the NEXT kernel begin
+// to launch as this grid's CTAs exit.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -395,6 +401,25 @@ inline int make_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t row
   NLAM_REQUIRE(r == CUDA_SUCCESS, NLAM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p cols=%llu rows=%llu", (int)r, ptr,
                (unsigned long long)cols, (unsigned long long)rows);
   return NLAM_OK;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (NLAM_NO_PDL=1: without)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  static int pdl = -1;
+  if (pdl < 0) pdl = getenv("NLAM_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }

@@ -489,6 +489,9 @@ def _boundary_blocks(mask, max_blocks=8, min_saving=0.2):
     """Row runs of a (G,) boundary mask as copy blocks ``(start node, run length, pitch, count)``: ``count`` runs of
     ``run length`` nodes, ``pitch`` nodes apart (count == 1: a single run).  None when the mask is not worth compacting
     (everything selected, too fragmented for a handful of strided copies, or the strips do not tile the grid evenly)."""
+    import os
+    if os.environ.get("NLAM_NO_BOUNDARY_COMPACTION"):
+        return None
     m = (mask.reshape(-1) > 0).to("cpu").numpy().astype("int8")
     G = m.shape[0]
     if G == 0 or m.sum() == 0 or m.sum() > (1.0 - min_saving) * G:
