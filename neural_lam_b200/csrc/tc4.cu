@@ -116,12 +116,12 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_init(bar_w, 1);
       mbar_init(bar_wscaled, EPI);
       for (int t = 0; t < NR; ++t) {
-        mbar_init(bar_ring_full + 8 * t, p.in_narrow ? EPI : 1);  // repack threads / TMA transactions
+        mbar_init(bar_ring_full + 8 * t, p.in_narrow ? 2 * EPI : 1);  // repack threads / TMA transactions
         mbar_init(bar_ring_free + 8 * t, 1);
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(bar_st_full + 8 * t, 1);
-        mbar_init(bar_st_free + 8 * t, EPI);
+        mbar_init(bar_st_free + 8 * t, 2 * EPI);
       }
       for (int t = 0; t < NT; ++t) {
         mbar_init(bar_d1_full + 8 * t, 1);
@@ -185,23 +185,25 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   auto op_phase = [&](int ti, int s) -> uint32_t {
     return (uint32_t)(p.in_narrow ? (ti / 3) & 1 : ((ti * n_src + s) / NR) & 1);
   };
-  // narrow inputs: the 256 threads of the epilogue-1 group repack tile ti from the flat staging slot into the K-major
-  // swizzled operand tile (thread = row x one 32-column block; columns k_real..63 are zero).  Two warps did this before:
-  // 450 instructions per thread and tile in series, 6.2 k cycles per tile — the whole kernel waited for them.
-  auto repack_tile = [&](int ti, int gt, bool lead) {
+  // narrow inputs: BOTH epilogue groups repack tile ti from the flat staging slot into the K-major swizzled operand tile: group
+  // grp fills the 32-column block grp (thread = row x four 16-byte chunks; columns k_real..63 are zero).  History: two dedicated
+  // warps (450 instructions per thread and tile in series, 6.2 k cycles per tile: 351 us), then the epilogue-1 group alone
+  // (SiLU 1.3 k + repack 1.4 k cycles per tile while epilogue 2 idled half the time: 219 us).
+  auto repack_tile = [&](int ti, int gt, bool lead, int grp) {
     const int st = ti & 1;
     const int slot = op_slot(ti, 0);
     if (lead) {
       mbar_wait(bar_st_full + 8 * st, (uint32_t)((ti >> 1) & 1));
       mbar_wait(bar_ring_free + 8 * slot, op_phase(ti, 0) ^ 1u);
     }
-    named_bar_sync(1, EPI);
+    named_bar_sync(1 + grp, EPI);
     uint8_t* tile = smem + OFF_RING + slot * 2 * BLK;
     const float* stg = reinterpret_cast<const float*>(smem + OFF_RING + st * 2 * BLK);
-    const int row = gt & 127, hh = gt >> 7;
+    const int row = gt & 127, hh = grp, c4 = 4 * (gt >> 7);
     const int rx = row & 7;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {  // one 16-byte chunk of the operand row per store
+    for (int cq = 0; cq < 4; ++cq) {  // one 16-byte chunk of the operand row per store
+      const int ch = c4 + cq;
       float4 o;
       float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
@@ -395,8 +397,8 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
     const int gt1 = tid - W_E1 * 32;
     if (p.in_narrow) {  // operand tiles are repacked two tiles ahead of their SiLU
-      if (n_my > 0) repack_tile(0, gt1, lead);
-      if (n_my > 1) repack_tile(1, gt1, lead);
+      if (n_my > 0) repack_tile(0, gt1, lead, 0);
+      if (n_my > 1) repack_tile(1, gt1, lead, 0);
     }
     for (int ti = 0; ti < n_my; ++ti) {
       const int ts = ti % NT;
@@ -434,7 +436,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       tmem_st32(d1 + 64, v);
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
-      if (p.in_narrow && ti + 2 < n_my) repack_tile(ti + 2, gt1, lead);
+      if (p.in_narrow && ti + 2 < n_my) repack_tile(ti + 2, gt1, lead, 0);
     }
   } else if (warp < W_E1) {
     // =============================== epilogue 2: bias, LayerNorm, residual; output in place over the source tile ===
@@ -452,6 +454,10 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int c = c0 + 2 * i;
       const int nb = p.out_narrow ? p.out_narrow : 64;
       b2r[i] = make_float2(c < nb ? __ldg(p.b2 + c) : 0.f, c + 1 < nb ? __ldg(p.b2 + c + 1) : 0.f);
+    }
+    if (p.in_narrow) {  // this group's column block of the first two operand tiles
+      if (n_my > 0) repack_tile(0, tid, warp == 0, 1);
+      if (n_my > 1) repack_tile(1, tid, warp == 0, 1);
     }
     for (int ti = 0; ti < n_my; ++ti) {
       const int ts = ti % NT;
@@ -496,6 +502,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         fence_proxy_async();
         mbar_arrive(bar_staged + 8 * ts);
         if (tid == 0) R4_DBG(6, ti);
+        if (p.in_narrow && ti + 2 < n_my) repack_tile(ti + 2, tid, warp == 0, 1);
         continue;
       }
       if (warp == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((ti / NT) & 1));
@@ -546,6 +553,7 @@ tc_rowmlp64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       fence_proxy_async();
       mbar_arrive(bar_staged + 8 * ts);
       if (tid == 0) R4_DBG(6, ti);
+      if (p.in_narrow && ti + 2 < n_my) repack_tile(ti + 2, tid, warp == 0, 1);
     }
   }
 
