@@ -357,6 +357,10 @@ tc_edge_bcast_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       const int cg = gt & 15, g = gt >> 4;
       const uint8_t* mbase = smem + OFF_RING + r * 2 * BLK + (cg >> 3) * BLK;
       const int chq = cg & 7;
+      // LayerNorm's affine part is applied here, once per receiver and column, instead of once per edge in epilogue 2:
+      // sum_e (gamma*n_e + beta) = gamma * sum_e n_e + deg * beta  (this kernel never writes the messages themselves)
+      const float4 gam = *reinterpret_cast<const float4*>(sprm + 64 + 4 * cg);
+      const float4 bet = *reinterpret_cast<const float4*>(sprm + 128 + 4 * cg);
       for (int j = g; j < nrec; j += EPI / 16) {
         const int k0 = lp[j], k1 = lp[j + 1];
         // rows k0..k1-1 in CSR order, as two interleaved chains (even / odd position) of packed adds
@@ -378,13 +382,19 @@ tc_edge_bcast_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         a0 = add2(a0, b0);
         a1 = add2(a1, b1);
         float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+        float cnt = (float)(k1 - k0);
         if (p.mean) {
           const float sc = 1.0f / (float)max(k1 - k0, 1);
           acc.x *= sc;
           acc.y *= sc;
           acc.z *= sc;
           acc.w *= sc;
+          cnt = k1 > k0 ? 1.f : 0.f;
         }
+        acc.x = fmaf(acc.x, gam.x, cnt * bet.x);
+        acc.y = fmaf(acc.y, gam.y, cnt * bet.y);
+        acc.z = fmaf(acc.z, gam.z, cnt * bet.z);
+        acc.w = fmaf(acc.w, gam.w, cnt * bet.w);
         *reinterpret_cast<float4*>(p.aggr + ((long long)br * p.n_rec + r0 + j) * 64 + cg * 4) = acc;
       }
       mbar_arrive(bar_free + 8 * r);  // this thread is done with the slot (and its offsets)
@@ -528,11 +538,9 @@ tc_edge_bcast_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
         uint8_t* mrow = smem + OFF_RING + r * 2 * BLK + half * BLK + rsw;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 g4 = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k);
-          const float4 b4 = *reinterpret_cast<const float4*>(sprm + 128 + c0 + 4 * k);
-          const float2 m0 = fma2(fma2(v[2 * k], rs2, nm2), make_float2(g4.x, g4.y), make_float2(b4.x, b4.y));
-          const float2 m1 = fma2(fma2(v[2 * k + 1], rs2, nm2), make_float2(g4.z, g4.w), make_float2(b4.z, b4.w));
+        for (int k = 0; k < 8; ++k) {  // normalised values only: gamma / beta follow the segmented sum
+          const float2 m0 = fma2(v[2 * k], rs2, nm2);
+          const float2 m1 = fma2(v[2 * k + 1], rs2, nm2);
           *reinterpret_cast<float4*>(mrow + ((k ^ rxs) << 4)) = make_float4(m0.x, m0.y, m1.x, m1.y);
         }
       }

@@ -74,7 +74,8 @@ struct Edge8Params {
     if (p.dbg && blockIdx.x == 1 && (it) >= 40 && (it) < 56) p.dbg[((it) - 40) * 16 + (slot)] = clock64(); \
   } while (0)
 
-template <bool RNOW>
+// HAS_OUT: the edge tensor is updated in place (else: no edge output, and LayerNorm's affine part follows the segmented sum)
+template <bool HAS_OUT>
 __global__ void __launch_bounds__(e8::THREADS, 1)
 tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
@@ -114,7 +115,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
       }
       for (int s = 0; s < NW; ++s) {
         mbar_init(bar_w_full + 8 * s, 1);
-        mbar_init(bar_w_free + 8 * s, EPI + (p.has_out ? 1 : 0));
+        mbar_init(bar_w_free + 8 * s, EPI + (HAS_OUT ? 1 : 0));
       }
       for (int s = 0; s < 6; ++s) mbar_init(bar_staged + 8 * s, EPI);
       for (int s = 0; s < NT; ++s) {
@@ -136,7 +137,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmPs) : "memory");
-    if (p.has_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+    if (HAS_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
   pdl_launch_dependents();
   pdl_wait();  // everything below may read what the previous kernel in the stream wrote
@@ -159,7 +160,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
 
   if (warp == W_ST) {
     // =============================== e += m (TMA reduce-add of the staged messages) ===============================
-    if (p.has_out && lane == 0) {
+    if (HAS_OUT && lane == 0) {
       int t = t_first, b = b_first - 1, t_cur = -1, e0 = 0;
       for (int it = 0; it < n_my; ++it) {
         if (++b == p.B) {
@@ -186,7 +187,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
     // =============================== loaders (2 warps) ===============================
     const uint64_t pol_keep = policy_evict_last();
     // in place: the lines of the e tile should stay in L2 until the reduce-add reaches them
-    const uint64_t pol_e = p.has_out ? (p.e_policy ? policy_evict_last() : policy_evict_normal()) : policy_evict_first();
+    const uint64_t pol_e = HAS_OUT ? (p.e_policy ? policy_evict_last() : policy_evict_normal()) : policy_evict_first();
     const int lw = warp - W_LD;
     if (lw == 0 && lane == 0) {
       mbar_expect_tx(bar_w, 4u * WBLK);
@@ -369,12 +370,22 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
         a0 = add2(a0, b0);
         a1 = add2(a1, b1);
         float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+        float cnt = (float)(k1 - k0);
         if (p.mean) {
           const float sc = 1.0f / (float)max(k1 - k0, 1);
           acc.x *= sc;
           acc.y *= sc;
           acc.z *= sc;
           acc.w *= sc;
+          cnt = k1 > k0 ? 1.f : 0.f;
+        }
+        if (!HAS_OUT) {
+          const float4 gam = *reinterpret_cast<const float4*>(sprm + 64 + 4 * cg);
+          const float4 bet = *reinterpret_cast<const float4*>(sprm + 128 + 4 * cg);
+          acc.x = fmaf(acc.x, gam.x, cnt * bet.x);
+          acc.y = fmaf(acc.y, gam.y, cnt * bet.y);
+          acc.z = fmaf(acc.z, gam.z, cnt * bet.z);
+          acc.w = fmaf(acc.w, gam.w, cnt * bet.w);
         }
         *reinterpret_cast<float4*>(p.aggr + ((long long)br * p.n_rec + r0 + j) * 64 + cg * 4) = acc;
       }
@@ -447,7 +458,7 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
       tc_fence_before();
       mbar_arrive(bar_hb_full + 8 * ts);
       if (gt == 0) E8_DBG(4, it);
-      if (!RNOW && prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
+      if (prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
 
       // ---- epilogue 2: bias, LayerNorm -> messages into the item's window slot (epilogue 1 has consumed the window)
       if (lane == 0) mbar_wait(bar_d2_full + 8 * ts, (uint32_t)((it / NT) & 1));
@@ -487,7 +498,16 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
         const float rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + p.eps);
         const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mu * rstd, -mu * rstd);
         uint8_t* mrow = smem + OFF_WIN + sw * 2 * BLK + half * BLK + rsw;
-        if (row < ne_cur) {
+        if (!HAS_OUT) {
+          // no edge output: only the aggregate is needed, and sum_e (gamma*n_e + beta) = gamma * sum_e n_e + deg * beta — the
+          // affine part is applied once per receiver after the segmented sum (rows past the tile's edges are never summed)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 m0 = fma2(v[2 * k], rs2, nm2);
+            const float2 m1 = fma2(v[2 * k + 1], rs2, nm2);
+            *reinterpret_cast<float4*>(mrow + ((k ^ rxs) << 4)) = make_float4(m0.x, m0.y, m1.x, m1.y);
+          }
+        } else if (row < ne_cur) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float4 g4 = *reinterpret_cast<const float4*>(sprm + 64 + c0 + 4 * k);
@@ -503,20 +523,16 @@ tc_edge_rmw_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
           for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(mrow + (k << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      if (p.has_out) fence_proxy_async();
+      if (HAS_OUT) fence_proxy_async();
       mbar_arrive(bar_staged + 8 * (it % 6));
       if (gt == 0) E8_DBG(6, it);
-      if (RNOW) {  // measured slower (269 vs 254 us): the group idles while the second GEMM runs
-        reduce_item(it, sw, b, r0_cur, nrec_cur);
-        continue;
-      }
       prev_it = it;
       prev_sw = sw;
       prev_b = b;
       prev_r0 = r0_cur;
       prev_nrec = nrec_cur;
     }
-    if (!RNOW && prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
+    if (prev_it >= 0) reduce_item(prev_it, prev_sw, prev_b, prev_r0, prev_nrec);
   }
 
   tc_fence_before();
@@ -609,11 +625,6 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
     epol = e ? atoi(e) : 1;  // measured: 242 vs 254 us, 691 vs 708 MB read from DRAM
   }
   p.e_policy = epol;
-  static int rnow = -1;
-  if (rnow < 0) {
-    const char* e = getenv("NLAM_E8_RNOW");
-    rnow = e ? atoi(e) : 0;
-  }
   const int grid = (int)((n_work + p.items_per_cta - 1) / p.items_per_cta);
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
@@ -625,8 +636,7 @@ int tc_edge_rmw(const NlamGraph* g, const NlamMlp* edge_mlp, const float* send, 
   }
   {
     ProfScope ps("tc_edge_rmw_kernel", st, edge_algorithmic_bytes(g, B, send_bs, rec_bs, edge_bs, edge_out != nullptr, 64));
-    // RNOW: segmented sum of an item right after its epilogue 2 (else after epilogue 1 of the group's next item)
-    if (rnow)
+    if (edge_out)
       NLAM_CUDA_OK(launch_pdl(tc_edge_rmw_kernel<true>, grid, e8::THREADS, e8::SMEM, st, me, mw1, mw2, me, mps, p));
     else
       NLAM_CUDA_OK(launch_pdl(tc_edge_rmw_kernel<false>, grid, e8::THREADS, e8::SMEM, st, me, mw1, mw2, me, mps, p));
